@@ -1,0 +1,663 @@
+// genrec_b200 - C ABI (include/genrec_b200.h): argument checking, buffer carving and kernel orchestration.
+// Nothing here allocates or synchronises; every kernel goes onto the caller's stream.
+#include "../../include/genrec_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "attn_hstu.cuh"
+#include "attn_sasrec.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+#include "rq_argmin.cuh"
+
+using namespace grb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define GRB_CUDA(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return fail(GRB_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+#define GRB_REQUIRE(cond, ...)                            \
+    do {                                                  \
+        if (!(cond)) return fail(GRB_EINVAL, __VA_ARGS__); \
+    } while (0)
+#define GRB_TRY(expr)          \
+    do {                       \
+        int _r = (expr);       \
+        if (_r != 0) return _r; \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+int row_grid(int T) {
+    int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+    int cap = sm_count() * 8;
+    return need < cap ? (need < 1 ? 1 : need) : cap;
+}
+int splitk_for(int M, int N, int K) {
+    int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN);
+    int want = (2 * sm_count() + tiles - 1) / tiles;
+    int kt = (K + GEMM_BK - 1) / GEMM_BK;
+    int maxs = kt / 4 > 0 ? kt / 4 : 1;  // at least 4 k-tiles per split
+    return want < 1 ? 1 : (want > maxs ? maxs : want);
+}
+
+// ---- carved layouts ------------------------------------------------------------------------------------------
+struct LayerSaved {
+    bf16 *xb, *zp, *P, *O, *xn, *z1, *hact;
+    float *st1, *x1, *st2;
+    size_t bytes;
+};
+LayerSaved carve_saved(void* base, size_t T, size_t D) {
+    LayerSaved s;
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* p = b ? b + off : nullptr; off += align_up(n); return p; };
+    s.xb = (bf16*)take(T * D * 2);
+    s.zp = (bf16*)take(T * 4 * D * 2);
+    s.P = (bf16*)take(T * 4 * D * 2);
+    s.O = (bf16*)take(T * D * 2);
+    s.st1 = (float*)take(T * 2 * 4);
+    s.x1 = (float*)take(T * D * 4);
+    s.xn = (bf16*)take(T * D * 2);
+    s.st2 = (float*)take(T * 2 * 4);
+    s.z1 = (bf16*)take(T * 4 * D * 2);
+    s.hact = (bf16*)take(T * 4 * D * 2);
+    s.bytes = off;
+    return s;
+}
+struct LayerWork {
+    bf16 *dyb, *dz1, *dO, *dzp;
+    float *dxn, *dx1;
+    size_t bytes;
+};
+LayerWork carve_work(void* base, size_t T, size_t D) {
+    LayerWork w;
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* p = b ? b + off : nullptr; off += align_up(n); return p; };
+    w.dyb = (bf16*)take(T * D * 2);
+    w.dz1 = (bf16*)take(T * 4 * D * 2);
+    w.dxn = (float*)take(T * D * 4);
+    w.dx1 = (float*)take(T * D * 4);
+    w.dO = (bf16*)take(T * D * 2);
+    w.dzp = (bf16*)take(T * 4 * D * 2);
+    w.bytes = off;
+    return w;
+}
+
+int check_dims(const grb_hstu_dims* d) {
+    GRB_REQUIRE(d != nullptr, "dims is null");
+    GRB_REQUIRE(d->B > 0 && d->L > 0 && d->H > 0, "B, L, H must be positive (B=%d L=%d H=%d)", d->B, d->L, d->H);
+    GRB_REQUIRE(d->D == 64 || d->D == 128 || d->D == 256, "embed_dim %d unsupported (64, 128, 256)", d->D);
+    GRB_REQUIRE(d->D % d->H == 0, "embed_dim %% num_heads != 0");
+    int dh = d->D / d->H;
+    GRB_REQUIRE(dh == 32 || dh == 64, "head_dim %d unsupported (32, 64)", dh);
+    GRB_REQUIRE(d->npos >= 1 && d->npos <= ATT_MAX_BUCKETS, "num_position_buckets %d out of range [1,64]", d->npos);
+    GRB_REQUIRE(d->ntime >= 0 && d->ntime <= ATT_MAX_BUCKETS, "num_time_buckets %d out of range [0,64]", d->ntime);
+    GRB_REQUIRE(d->L <= 16384, "seq_len %d too long", d->L);
+    GRB_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
+    return 0;
+}
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, high-water mark): no runtime call on the steady-state path,
+// in particular none while a CUDA graph is being captured after warm-up.
+template <class Kern>
+int set_smem(Kern k, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> high_water;  // keyed by kernel address (same-signature kernels share this instance)
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& hw = high_water[reinterpret_cast<const void*>(k)];
+    if (hw < 48 * 1024) hw = 48 * 1024;
+    if (bytes > hw) {
+        GRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        hw = bytes;
+    }
+    return 0;
+}
+
+HstuAttnArgs make_attn_args(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s, const LayerSaved& sv) {
+    HstuAttnArgs a;
+    memset(&a, 0, sizeof(a));
+    const int D = d->D;
+    a.q = sv.P + 2 * D; a.k = sv.P + 3 * D; a.v = sv.P + D;
+    a.ldq = a.ldk = a.ldv = 4 * D;
+    a.pad = s->pad;
+    a.B = d->B; a.L = d->L; a.H = d->H;
+    a.bias.wpos = p->pos_table;
+    a.bias.pos_bucket = s->pos_bucket;
+    const bool has_time = p->time_table != nullptr && s->timestamps != nullptr && d->ntime > 0;
+    a.bias.wtime = has_time ? p->time_table : nullptr;
+    a.bias.time_thr = reinterpret_cast<const long long*>(s->time_thr);
+    a.bias.ts = has_time ? reinterpret_cast<const long long*>(s->timestamps) : nullptr;
+    a.bias.npos = d->npos;
+    a.bias.ntime = has_time ? d->ntime : 0;
+    a.o = sv.O; a.ldo = D;
+    return a;
+}
+
+template <int DH>
+int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
+    size_t smem = sizeof(AttSmem<DH>) + align_up(a.L, 16);
+    GRB_TRY(set_smem(hstu_attn_fwd_kernel<DH>, smem));
+    dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
+    hstu_attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(a, a.bias.pos_bucket);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int DH>
+int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
+    dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
+    size_t posb = align_up(a.L, 16);
+    size_t smem_q = sizeof(AttSmem<DH>) + posb;
+    GRB_TRY(set_smem(hstu_attn_bwd_dq_kernel<DH>, smem_q));
+    hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a, a.bias.pos_bucket);
+    GRB_CUDA(cudaGetLastError());
+    size_t smem_k = sizeof(AttSmem<DH>) + posb + (size_t)4 * (a.bias.ntime + a.bias.npos) * 32 * sizeof(float);
+    GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
+    hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, a.bias.pos_bucket, (int)posb);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NP, class Args, class Kern>
+int launch_row(Kern k, const Args& a, int T, cudaStream_t st) {
+    k<<<row_grid(T), ROW_THREADS, 0, st>>>(a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+#define GRB_ROW_DISPATCH(D, KERN, ARGS, T, ST)                                            \
+    do {                                                                                  \
+        if ((D) == 64) GRB_TRY((launch_row<1>(KERN<1>, ARGS, T, ST)));                    \
+        else if ((D) == 128) GRB_TRY((launch_row<2>(KERN<2>, ARGS, T, ST)));              \
+        else if ((D) == 256) GRB_TRY((launch_row<4>(KERN<4>, ARGS, T, ST)));              \
+        else return fail(GRB_EINVAL, "row kernels support D in {64,128,256}, got %d", (D)); \
+    } while (0)
+
+int cast_bf16(const float* in, bf16* out, size_t n, int D, const Dropout& drop, const float* row_scale, cudaStream_t st) {
+    GRB_REQUIRE(n % 4 == 0, "cast length must be a multiple of 4");
+    int threads = 256;
+    size_t blocks = (n / 4 + threads - 1) / threads;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    if (blocks < 1) blocks = 1;
+    cast_f32_bf16_kernel<<<(unsigned)blocks, threads, 0, st>>>(in, out, n, D, drop, row_scale);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int colsum(const bf16* in, int T, int N, int ld, float* out, cudaStream_t st) {
+    int cx = (N + 63) / 64;
+    int cy = (2 * sm_count() + cx - 1) / cx;
+    int maxy = (T + 63) / 64;
+    if (cy > maxy) cy = maxy;
+    if (cy < 1) cy = 1;
+    colsum_bf16_kernel<<<dim3(cx, cy), 256, 0, st>>>(in, T, N, ld, out);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+constexpr uint32_t SITE_GATE = 0, SITE_FFN_HID = 1, SITE_FFN_OUT = 2, SITE_EMBED = 250, SITE_ATTN = 3;
+inline uint32_t site_of(int layer, uint32_t which) { return (uint32_t)layer * 8u + which; }
+
+}  // namespace
+
+extern "C" {
+
+const char* grb_last_error(void) { return g_err; }
+int grb_version(void) { return 100; }
+
+int grb_check_device(int ordinal) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, ordinal);
+    if (e != cudaSuccess) return fail(GRB_ENODEV, "cudaGetDeviceProperties(%d): %s", ordinal, cudaGetErrorString(e));
+    if (prop.major != 10) return fail(GRB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", ordinal, prop.major, prop.minor);
+    return 0;
+}
+
+size_t grb_hstu_layer_saved_bytes(const grb_hstu_dims* d) {
+    if (check_dims(d)) return 0;
+    return carve_saved(nullptr, (size_t)d->B * d->L, d->D).bytes;
+}
+size_t grb_hstu_layer_workspace_bytes(const grb_hstu_dims* d) {
+    if (check_dims(d)) return 0;
+    return carve_work(nullptr, (size_t)d->B * d->L, d->D).bytes;
+}
+
+int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s, const float* x,
+                           float* y, void* saved, void* stream) {
+    GRB_TRY(check_dims(d));
+    GRB_REQUIRE(p && s && x && y && saved, "null argument");
+    GRB_REQUIRE(p->proj_w && p->proj_b && p->pos_table && p->ln1_g && p->ln1_b && p->ffn1_w && p->ffn1_b && p->ffn2_w &&
+                    p->ffn2_b && p->ln2_g && p->ln2_b, "null parameter pointer");
+    GRB_REQUIRE(s->pad && s->pos_bucket && s->time_thr, "null sequence metadata");
+    GRB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(saved) && aligned16(p->proj_w) && aligned16(p->ffn1_w) && aligned16(p->ffn2_w),
+                "buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = d->B * d->L, D = d->D;
+    LayerSaved sv = carve_saved(saved, T, D);
+    const Dropout nodrop = make_dropout(0.f, 0, 0);
+
+    // 1. bf16 copy of the block input (GEMM operand; also the dWp operand in backward)
+    GRB_TRY(cast_bf16(x, sv.xb, (size_t)T * D, D, nodrop, nullptr, st));
+    // 2. P = silu(x Wp^T + bp) -> [U | V | Q | K]                                            (hstu.py:234-235)
+    {
+        EpiBiasSilu epi{p->proj_b, sv.zp, sv.P, 4 * D, nodrop};
+        GRB_CUDA((launch_gemm<0, 0>(sv.xb, (const bf16*)p->proj_w, T, 4 * D, D, D, D, 1, epi, st)));
+    }
+    // 3. O = silu(Q K^T + bias) V, causal + key padding                                      (hstu.py:244-267)
+    {
+        HstuAttnArgs a = make_attn_args(d, p, s, sv);
+        if (D / d->H == 32) GRB_TRY(launch_hstu_attn_fwd<32>(a, st));
+        else GRB_TRY(launch_hstu_attn_fwd<64>(a, st));
+    }
+    // 4. x1 = x + drop(LN1(O) * U) ; xn = LN2(x1)                                            (hstu.py:271-278)
+    {
+        LnGateFwdArgs a{sv.O, D, sv.P, 4 * D, x, p->ln1_g, p->ln1_b, p->ln2_g, p->ln2_b, sv.x1, sv.xn, sv.st1, sv.st2, T, D, 1e-5f,
+                        make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_GATE), d->seed_dev)};
+        GRB_ROW_DISPATCH(D, ln_gate_fwd_kernel, a, T, st);
+    }
+    // 5. h = drop(silu(xn W1^T + b1))                                                        (hstu.py:210-212)
+    {
+        EpiBiasSilu epi{p->ffn1_b, sv.z1, sv.hact, 4 * D, make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_HID), d->seed_dev)};
+        GRB_CUDA((launch_gemm<0, 0>(sv.xn, (const bf16*)p->ffn1_w, T, 4 * D, D, D, D, 1, epi, st)));
+    }
+    // 6. y = x1 + drop(h W2^T + b2)                                                          (hstu.py:213-214, :278)
+    {
+        EpiBiasResidual epi{p->ffn2_b, sv.x1, y, nullptr, D, make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_OUT), d->seed_dev)};
+        GRB_CUDA((launch_gemm<0, 0>(sv.hact, (const bf16*)p->ffn2_w, T, D, 4 * D, 4 * D, 4 * D, 1, epi, st)));
+    }
+    return 0;
+}
+
+int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s, const float* dy,
+                            const void* saved, float* dx, const grb_hstu_layer_grads* g, void* workspace, void* stream) {
+    GRB_TRY(check_dims(d));
+    GRB_REQUIRE(p && s && dy && saved && dx && g && workspace, "null argument");
+    GRB_REQUIRE(g->proj_w && g->proj_b && g->pos_table && g->ln1_g && g->ln1_b && g->ffn1_w && g->ffn1_b && g->ffn2_w && g->ffn2_b &&
+                    g->ln2_g && g->ln2_b, "null gradient pointer");
+    GRB_REQUIRE(aligned16(dy) && aligned16(dx) && aligned16(saved) && aligned16(workspace), "buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = d->B * d->L, D = d->D;
+    LayerSaved sv = carve_saved(const_cast<void*>(saved), T, D);
+    LayerWork w = carve_work(workspace, T, D);
+    const Dropout nodrop = make_dropout(0.f, 0, 0);
+    const Dropout drop_out = make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_OUT), d->seed_dev);
+    const Dropout drop_hid = make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_HID), d->seed_dev);
+    const Dropout drop_gate = make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_GATE), d->seed_dev);
+
+    // FFN second linear
+    GRB_TRY(cast_bf16(dy, w.dyb, (size_t)T * D, D, drop_out, nullptr, st));
+    GRB_TRY(colsum(w.dyb, T, D, D, g->ffn2_b, st));
+    {
+        EpiAtomicF32 epi{g->ffn2_w, 4 * D, 1.f};  // dW2[D,4D] += dyb^T h
+        GRB_CUDA((launch_gemm<1, 1>(w.dyb, sv.hact, D, 4 * D, T, D, 4 * D, splitk_for(D, 4 * D, T), epi, st)));
+    }
+    {
+        EpiDAct<0> epi{sv.z1, w.dz1, 4 * D, drop_hid};  // dz1 = dropmask(dyb W2) * silu'(z1)
+        GRB_CUDA((launch_gemm<0, 1>(w.dyb, (const bf16*)p->ffn2_w, T, 4 * D, D, D, 4 * D, 1, epi, st)));
+    }
+    // FFN first linear
+    GRB_TRY(colsum(w.dz1, T, 4 * D, 4 * D, g->ffn1_b, st));
+    {
+        EpiAtomicF32 epi{g->ffn1_w, D, 1.f};  // dW1[4D,D] += dz1^T xn
+        GRB_CUDA((launch_gemm<1, 1>(w.dz1, sv.xn, 4 * D, D, T, 4 * D, D, splitk_for(4 * D, D, T), epi, st)));
+    }
+    {
+        EpiF32 epi{w.dxn, nullptr, D, 1.f};  // dxn = dz1 W1
+        GRB_CUDA((launch_gemm<0, 1>(w.dz1, (const bf16*)p->ffn1_w, T, D, 4 * D, 4 * D, D, 1, epi, st)));
+    }
+    // LN2 + residual + gate + LN1
+    {
+        LnGateBwdArgs a{dy, w.dxn, sv.x1, sv.st1, sv.st2, sv.O, D, sv.P, 4 * D, sv.zp, 4 * D, p->ln1_g, p->ln1_b, p->ln2_g,
+                        w.dx1, w.dO, D, w.dzp, 4 * D, g->ln1_g, g->ln1_b, g->ln2_g, g->ln2_b, T, D, drop_gate};
+        GRB_ROW_DISPATCH(D, ln_gate_bwd_kernel, a, T, st);
+    }
+    // attention backward -> gradients w.r.t. the V, Q, K pre-activations
+    {
+        HstuAttnArgs a = make_attn_args(d, p, s, sv);
+        a.d_o = w.dO; a.lddo = D;
+        a.zq = sv.zp + 2 * D; a.zk = sv.zp + 3 * D; a.zv = sv.zp + D; a.ldz = 4 * D;
+        a.dq = w.dzp + 2 * D; a.dk = w.dzp + 3 * D; a.dv = w.dzp + D; a.lddq = 4 * D;
+        a.dwpos = g->pos_table;
+        a.dwtime = g->time_table;
+        GRB_REQUIRE(a.bias.wtime == nullptr || g->time_table != nullptr, "time_table gradient pointer is null");
+        if (D / d->H == 32) GRB_TRY(launch_hstu_attn_bwd<32>(a, st));
+        else GRB_TRY(launch_hstu_attn_bwd<64>(a, st));
+    }
+    // projection
+    GRB_TRY(colsum(w.dzp, T, 4 * D, 4 * D, g->proj_b, st));
+    {
+        EpiAtomicF32 epi{g->proj_w, D, 1.f};  // dWp[4D,D] += dzp^T xb
+        GRB_CUDA((launch_gemm<1, 1>(w.dzp, sv.xb, 4 * D, D, T, 4 * D, D, splitk_for(4 * D, D, T), epi, st)));
+    }
+    {
+        EpiF32 epi{dx, w.dx1, D, 1.f};  // dx = dx1 + dzp Wp
+        GRB_CUDA((launch_gemm<0, 1>(w.dzp, (const bf16*)p->proj_w, T, D, 4 * D, 4 * D, D, 1, epi, st)));
+    }
+    (void)nodrop;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+int grb_embed_forward(const int64_t* ids, const float* table, const float* pos_table, float* x, uint8_t* pad, int B, int L, int D,
+                      float scale, int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+    GRB_REQUIRE(ids && table && x, "null argument");
+    GRB_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, "bad shape");
+    EmbedArgs a{reinterpret_cast<const long long*>(ids), table, pos_table, x, pad, B * L, L, D, scale, mask_pad_rows,
+                make_dropout(dropout_p, seed, SITE_EMBED, seed_dev)};
+    embed_fwd_kernel<<<row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float* dpos_table, int B, int L, int D, float scale,
+                       int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+    GRB_REQUIRE(ids && dx && dtable, "null argument");
+    EmbedBwdArgs a{reinterpret_cast<const long long*>(ids), dx, dtable, dpos_table, B * L, L, D, scale, mask_pad_rows,
+                   make_dropout(dropout_p, seed, SITE_EMBED, seed_dev)};
+    embed_bwd_kernel<<<row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ head
+namespace {
+struct HeadWork {
+    bf16* xf; float* stf; bf16* logits; float* dxf; float* scal;  // scal[0] = inv_count
+    int ldl;
+    size_t bytes;
+};
+HeadWork carve_head(void* base, size_t T, size_t D, size_t C) {
+    HeadWork h;
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* p = b ? b + off : nullptr; off += align_up(n); return p; };
+    h.ldl = (int)((C + 7) / 8 * 8);
+    h.xf = (bf16*)take(T * D * 2);
+    h.stf = (float*)take(T * 2 * 4);
+    h.dxf = (float*)take(T * D * 4);
+    h.scal = (float*)take(64);
+    h.logits = (bf16*)take(T * (size_t)h.ldl * 2);
+    h.bytes = off;
+    return h;
+}
+}  // namespace
+
+size_t grb_head_workspace_bytes(int T, int D, int C) { return carve_head(nullptr, T, D, C).bytes; }
+
+int grb_head_loss_forward_backward(const float* x, const float* ln_g, const float* ln_b, float ln_eps, const void* table_bf16,
+                                   const int64_t* targets, int T, int D, int C, float* loss, float* dx, float* dtable, float* dln_g,
+                                   float* dln_b, void* workspace, void* stream) {
+    GRB_REQUIRE(x && ln_g && ln_b && table_bf16 && targets && loss && workspace, "null argument");
+    GRB_REQUIRE(T > 0 && C > 1 && (D == 64 || D == 128 || D == 256), "bad shape T=%d D=%d C=%d", T, D, C);
+    const bool want_grad = dx != nullptr;
+    GRB_REQUIRE(!want_grad || (dtable && dln_g && dln_b), "null gradient pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    HeadWork h = carve_head(workspace, T, D, C);
+    {
+        LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
+        GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
+    }
+    {
+        EpiBf16 epi{h.logits, h.ldl};  // logits = xf E^T                                      (hstu.py:137)
+        GRB_CUDA((launch_gemm<0, 0>(h.xf, (const bf16*)table_bf16, T, C, D, D, D, 1, epi, st)));
+    }
+    ce_count_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(targets), T, h.scal, loss);
+    GRB_CUDA(cudaGetLastError());
+    ce_fwd_bwd_kernel<<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
+    GRB_CUDA(cudaGetLastError());
+    if (!want_grad) return 0;
+    {
+        EpiF32 epi{h.dxf, nullptr, D, 1.f};  // dxf = dlogits E
+        GRB_CUDA((launch_gemm<0, 1>(h.logits, (const bf16*)table_bf16, T, D, C, h.ldl, D, 1, epi, st)));
+    }
+    {
+        EpiAtomicF32 epi{dtable, D, 1.f};  // dE[C,D] += dlogits^T xf
+        GRB_CUDA((launch_gemm<1, 1>(h.logits, h.xf, C, D, T, h.ldl, D, splitk_for(C, D, T), epi, st)));
+    }
+    {
+        LnBwdArgs a{h.dxf, x, h.stf, ln_g, nullptr, dx, dln_g, dln_b, T, D};
+        GRB_ROW_DISPATCH(D, ln_bwd_kernel, a, T, st);
+    }
+    return 0;
+}
+
+int grb_head_logits(const float* x, const float* ln_g, const float* ln_b, float ln_eps, const void* table_bf16, int T, int D, int C,
+                    float* logits, void* workspace, void* stream) {
+    GRB_REQUIRE(x && ln_g && ln_b && table_bf16 && logits && workspace, "null argument");
+    GRB_REQUIRE(T > 0 && C > 1 && (D == 64 || D == 128 || D == 256), "bad shape T=%d D=%d C=%d", T, D, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    HeadWork h = carve_head(workspace, T, D, C);
+    {
+        LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
+        GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
+    }
+    EpiF32Scalar epi{logits, C, C};
+    GRB_CUDA((launch_gemm<0, 0>(h.xf, (const bf16*)table_bf16, T, C, D, D, D, 1, epi, st)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ SASRec attention
+namespace {
+int sas_args(const grb_sasrec_dims* d, SasAttnArgs& a) {
+    GRB_REQUIRE(d && d->B > 0 && d->L > 0 && d->H > 0 && d->D % d->H == 0, "bad dims");
+    int dh = d->D / d->H;
+    GRB_REQUIRE(dh == 32 || dh == 64, "head_dim %d unsupported (32, 64)", dh);
+    GRB_REQUIRE(d->D % 8 == 0, "embed_dim must be a multiple of 8");
+    memset(&a, 0, sizeof(a));
+    a.ld = d->D; a.B = d->B; a.L = d->L; a.H = d->H;
+    a.scale = 1.f / sqrtf((float)dh);
+    a.drop = make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_ATTN), d->seed_dev);
+    return 0;
+}
+}  // namespace
+
+int grb_sasrec_attention_forward(const grb_sasrec_dims* d, const void* q, const void* k, const void* v, const uint8_t* pad, void* out,
+                                 float* lse, void* stream) {
+    SasAttnArgs a;
+    GRB_TRY(sas_args(d, a));
+    GRB_REQUIRE(q && k && v && pad && out && lse, "null argument");
+    a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.pad = pad; a.out = (bf16*)out; a.lse = lse;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
+    if (d->D / d->H == 32) {
+        GRB_TRY(set_smem(sas_attn_fwd_kernel<32>, sizeof(SasSmem<32>)));
+        sas_attn_fwd_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
+    } else {
+        GRB_TRY(set_smem(sas_attn_fwd_kernel<64>, sizeof(SasSmem<64>)));
+        sas_attn_fwd_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
+    }
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int grb_sasrec_attention_backward(const grb_sasrec_dims* d, const void* q, const void* k, const void* v, const uint8_t* pad,
+                                  const void* out, const float* lse, const void* dout, void* dq, void* dk, void* dv, void* stream) {
+    SasAttnArgs a;
+    GRB_TRY(sas_args(d, a));
+    GRB_REQUIRE(q && k && v && pad && out && lse && dout && dq && dk && dv, "null argument");
+    a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.pad = pad;
+    a.out = (bf16*)const_cast<void*>(out); a.lse = const_cast<float*>(lse); a.d_out = (const bf16*)dout;
+    a.dq = (bf16*)dq; a.dk = (bf16*)dk; a.dv = (bf16*)dv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
+    if (d->D / d->H == 32) {
+        GRB_TRY(set_smem(sas_attn_bwd_dq_kernel<32>, sizeof(SasSmem<32>)));
+        GRB_TRY(set_smem(sas_attn_bwd_dkdv_kernel<32>, sizeof(SasSmem<32>)));
+        sas_attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
+        sas_attn_bwd_dkdv_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
+    } else {
+        GRB_TRY(set_smem(sas_attn_bwd_dq_kernel<64>, sizeof(SasSmem<64>)));
+        GRB_TRY(set_smem(sas_attn_bwd_dkdv_kernel<64>, sizeof(SasSmem<64>)));
+        sas_attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
+        sas_attn_bwd_dkdv_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
+    }
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ generic fused linear pieces
+int grb_linear_forward(const void* x_bf16, const void* w_bf16, const float* bias, int T, int N, int K, int act, void* z_bf16,
+                       void* act_bf16, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream) {
+    GRB_REQUIRE(x_bf16 && w_bf16 && bias && z_bf16, "null argument");
+    GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dropout drop = make_dropout(dropout_p, seed, site, seed_dev);
+    if (act == 0) {
+        EpiBiasBf16 epi{bias, (bf16*)z_bf16, N};
+        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
+    } else if (act == 1) {
+        GRB_REQUIRE(act_bf16, "act output is null");
+        EpiBiasSilu epi{bias, (bf16*)z_bf16, (bf16*)act_bf16, N, drop};
+        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
+    } else if (act == 2) {
+        GRB_REQUIRE(act_bf16, "act output is null");
+        EpiBiasRelu epi{bias, (bf16*)z_bf16, (bf16*)act_bf16, N, drop};
+        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
+    } else {
+        return fail(GRB_EINVAL, "unknown activation %d", act);
+    }
+    return 0;
+}
+int grb_linear_residual_forward(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual, const float* row_scale,
+                                int T, int N, int K, float* y, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                void* stream) {
+    GRB_REQUIRE(x_bf16 && w_bf16 && bias && residual && y, "null argument");
+    GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
+    EpiBiasResidual epi{bias, residual, y, row_scale, N, make_dropout(dropout_p, seed, site, seed_dev)};
+    GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, static_cast<cudaStream_t>(stream))));
+    return 0;
+}
+int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_bf16, int T, int N, int K, float* dx_f32,
+                        const float* dx_residual, float* dw, float* db, void* stream) {
+    GRB_REQUIRE(dy_bf16 && w_bf16, "null argument");
+    GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (db) GRB_TRY(colsum((const bf16*)dy_bf16, T, N, N, db, st));
+    if (dw) {
+        GRB_REQUIRE(x_bf16, "x is null");
+        EpiAtomicF32 epi{dw, K, 1.f};
+        GRB_CUDA((launch_gemm<1, 1>((const bf16*)dy_bf16, (const bf16*)x_bf16, N, K, T, N, K, splitk_for(N, K, T), epi, st)));
+    }
+    if (dx_f32) {
+        EpiF32 epi{dx_f32, dx_residual, K, 1.f};
+        GRB_CUDA((launch_gemm<0, 1>((const bf16*)dy_bf16, (const bf16*)w_bf16, T, K, N, N, K, 1, epi, st)));
+    }
+    return 0;
+}
+
+namespace {
+__global__ void dact_kernel(bf16* g, const bf16* z, size_t n, int act) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    for (; i < n; i += stride) {
+        float2 gv = unpack_bf16(*reinterpret_cast<const uint32_t*>(g + i));
+        float2 zv = unpack_bf16(*reinterpret_cast<const uint32_t*>(z + i));
+        float d0 = act == 1 ? dsiluf(zv.x) : (zv.x > 0.f ? 1.f : 0.f);
+        float d1 = act == 1 ? dsiluf(zv.y) : (zv.y > 0.f ? 1.f : 0.f);
+        *reinterpret_cast<uint32_t*>(g + i) = pack_bf16(gv.x * d0, gv.y * d1);
+    }
+}
+}  // namespace
+int grb_dact(const void* g_bf16_in_out, const void* z_bf16, size_t n, int act, void* stream) {
+    GRB_REQUIRE(g_bf16_in_out && z_bf16 && n % 2 == 0 && (act == 1 || act == 2), "bad argument");
+    size_t blocks = (n / 2 + 255) / 256;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    dact_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, static_cast<cudaStream_t>(stream)>>>((bf16*)const_cast<void*>(g_bf16_in_out), (const bf16*)z_bf16, n, act);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int grb_layernorm_forward(const float* x, const float* g, const float* b, float eps, int T, int D, void* y_bf16, float* y_f32,
+                          float* stats, void* stream) {
+    GRB_REQUIRE(x && g && b && (y_bf16 || y_f32), "null argument");
+    LnFwdArgs a{x, g, b, (bf16*)y_bf16, y_f32, stats, T, D, eps};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
+    return 0;
+}
+int grb_layernorm_backward(const float* dy, const float* x, const float* stats, const float* g, const float* residual, int T, int D,
+                           float* dx, float* dg, float* db, void* stream) {
+    GRB_REQUIRE(dy && x && stats && g && dx && dg && db, "null argument");
+    LnBwdArgs a{dy, x, stats, g, residual, dx, dg, db, T, D};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GRB_ROW_DISPATCH(D, ln_bwd_kernel, a, T, st);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer / casts
+int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream) {
+    GRB_REQUIRE(in && out_bf16, "null argument");
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    cast_flat_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (bf16*)out_bf16, n);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n, float* state, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, int zero_grad, void* stream) {
+    GRB_REQUIRE(p && g && m && v && state, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+    GRB_CUDA(cudaGetLastError());
+    if (n == 0) return 0;
+    AdamArgs a{p, g, m, v, (bf16*)p_bf16, n, state, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grad};
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ RQ-VAE
+int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, int D, int K, int levels, float commitment, int64_t* ids,
+                           float* emb, float* res, float* loss, float* res_out, void* stream) {
+    GRB_REQUIRE(x && codebooks && ids, "null argument");
+    GRB_REQUIRE(N >= 0 && levels >= 1 && K >= 2 && K % 2 == 0, "bad shape N=%lld K=%d levels=%d", (long long)N, K, levels);
+    GRB_REQUIRE(D == 32 || D == 64, "latent dim %d unsupported (32, 64)", D);
+    GRB_REQUIRE((size_t)K * (D + 1) * 4 <= 200 * 1024, "codebook level does not fit shared memory (K=%d, D=%d)", K, D);
+    GRB_REQUIRE(aligned16(x) && aligned16(codebooks), "buffers must be 16-byte aligned");
+    if (N == 0) return 0;
+    RqArgs a{x, codebooks, reinterpret_cast<long long*>(ids), emb, res, loss, res_out, (long long)N, K, levels, commitment};
+    size_t smem = (size_t)K * (D + 1) * sizeof(float);
+    unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (D == 32) {
+        GRB_TRY(set_smem(rq_residual_argmin_kernel<32>, smem));
+        rq_residual_argmin_kernel<32><<<grid, RQ_THREADS, smem, st>>>(a);
+    } else {
+        GRB_TRY(set_smem(rq_residual_argmin_kernel<64>, smem));
+        rq_residual_argmin_kernel<64><<<grid, RQ_THREADS, smem, st>>>(a);
+    }
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

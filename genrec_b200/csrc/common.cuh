@@ -1,0 +1,127 @@
+// genrec_b200 - shared device helpers (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace grb {
+
+typedef __nv_bfloat16 bf16;
+
+#define GRB_DEVINL __device__ __forceinline__
+
+// ----------------------------------------------------------------------------- small math
+GRB_DEVINL float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+GRB_DEVINL float siluf(float x) { return x * sigmoidf_fast(x); }
+// d/dx silu(x) = s * (1 + x * (1 - s))
+GRB_DEVINL float dsiluf(float x) {
+    float s = sigmoidf_fast(x);
+    return s * (1.f + x * (1.f - s));
+}
+
+GRB_DEVINL uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+GRB_DEVINL float2 unpack_bf16(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+GRB_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+GRB_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+GRB_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ----------------------------------------------------------------------------- dropout RNG
+// Counter-based: keep(seed, site, idx) is a pure function, so the backward pass re-derives the forward mask
+// instead of storing it.  One 64-bit mix (splitmix64 finaliser) per element -> 32 uniform bits.
+GRB_DEVINL uint32_t rng_u32(uint64_t seed, uint32_t site, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+struct Dropout {
+    uint64_t seed;
+    const unsigned long long* seed_dev;  // nullable: *seed_dev is added to seed at kernel start (CUDA-graph-safe reseeding)
+    uint32_t thresh;  // drop when rng < thresh ; thresh = p * 2^32
+    float scale;      // 1 / (1 - p) ; p == 0 -> thresh = 0, scale = 1
+    uint32_t site;
+    GRB_DEVINL void resolve() {
+        if (thresh != 0u && seed_dev) seed += *seed_dev;
+        seed_dev = nullptr;
+    }
+    GRB_DEVINL float apply(float v, uint64_t idx) const {
+        if (thresh == 0u) return v;
+        return rng_u32(seed, site, idx) < thresh ? 0.f : v * scale;
+    }
+};
+inline Dropout make_dropout(float p, uint64_t seed, uint32_t site, const void* seed_dev = nullptr) {
+    Dropout d;
+    d.seed = seed;
+    d.seed_dev = static_cast<const unsigned long long*>(seed_dev);
+    d.site = site;
+    if (p <= 0.f) {
+        d.thresh = 0u;
+        d.scale = 1.f;
+    } else {
+        double t = (double)p * 4294967296.0;
+        d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+        d.scale = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+// ----------------------------------------------------------------------------- async copy / ldmatrix / mma.sync
+GRB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16-byte global->shared async copy; src_bytes == 0 zero-fills the destination.
+GRB_DEVINL void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(src_bytes));
+}
+GRB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+GRB_DEVINL void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+GRB_DEVINL void ldsm_x4(uint32_t (&r)[4], const void* smem_row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row_ptr)));
+}
+GRB_DEVINL void ldsm_x4_t(uint32_t (&r)[4], const void* smem_row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row_ptr)));
+}
+
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+GRB_DEVINL void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Fragment address helpers (lane -> row/col of the 8x8 matrix row this lane points at), see DESIGN.md "mma.sync fragments".
+// A operand, smem tile stored [m][k] (k contiguous): non-transposed ldmatrix.
+GRB_DEVINL int lane_a_row(int lane) { return (lane & 7) + ((lane >> 3) & 1) * 8; }
+GRB_DEVINL int lane_a_col(int lane) { return (lane >> 4) * 8; }
+// B operand, smem tile stored [n][k] (k contiguous): non-transposed ldmatrix, two n-tiles per x4.
+GRB_DEVINL int lane_b_row(int lane) { return (lane & 7) + (lane >> 4) * 8; }
+GRB_DEVINL int lane_b_col(int lane) { return ((lane >> 3) & 1) * 8; }
+// B operand, smem tile stored [k][n] (n contiguous): transposed ldmatrix, two n-tiles per x4  (== lane_a_row/col).
+// A operand, smem tile stored [k][m] (m contiguous): transposed ldmatrix                      (== lane_b_row/col with row=k, col=m).
+
+}  // namespace grb

@@ -1,0 +1,494 @@
+// genrec_b200 - row-wise (per token) kernels: LayerNorm / gate / residual forward+backward, casts, column sums,
+// embedding gather/scatter, cross-entropy over bf16 logits, fused Adam.  HBM-bound; one warp per token row,
+// 8-byte (bf16x4 / float2) vector accesses, D % 64 == 0, D <= 512.
+#pragma once
+#include "common.cuh"
+
+namespace grb {
+
+constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows in flight per CTA
+
+struct LnStats { float mean, rstd; };
+
+// lane owns column pairs c = 2*lane + 64*p , p < NP
+template <int NP>
+GRB_DEVINL LnStats row_stats(const float (&v)[NP][2], int D, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) s += v[p][0] + v[p][1];
+    float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        float a = v[p][0] - mean, b = v[p][1] - mean;
+        q += a * a + b * b;
+    }
+    float var = warp_sum(q) / (float)D;
+    LnStats st;
+    st.mean = mean;
+    st.rstd = rsqrtf(var + eps);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------ HSTU: norm + gate + residual + norm
+//   N = LN1(O) ; x1 = x + drop(N * U) ; xn = LN2(x1)          (genrec/models/hstu.py:271-278)
+struct LnGateFwdArgs {
+    const bf16* O; int ldo;
+    const bf16* U; int ldu;
+    const float* x;
+    const float *g1, *b1, *g2, *b2;
+    float* x1; bf16* xn;
+    float* st1; float* st2;  // [T,2]
+    int T, D;
+    float eps;
+    Dropout drop;
+};
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS) ln_gate_fwd_kernel(LnGateFwdArgs a) {
+    a.drop.resolve();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        float o[NP][2], u[NP][2], xv[NP][2];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float2 t = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.O + (size_t)row * a.ldo + c));
+            o[p][0] = t.x; o[p][1] = t.y;
+            t = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.U + (size_t)row * a.ldu + c));
+            u[p][0] = t.x; u[p][1] = t.y;
+            float2 f = *reinterpret_cast<const float2*>(a.x + (size_t)row * a.D + c);
+            xv[p][0] = f.x; xv[p][1] = f.y;
+        }
+        LnStats s1 = row_stats<NP>(o, a.D, a.eps);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float n = (o[p][e] - s1.mean) * s1.rstd * a.g1[c + e] + a.b1[c + e];
+                xv[p][e] += a.drop.apply(n * u[p][e], (size_t)row * a.D + c + e);
+            }
+            *reinterpret_cast<float2*>(a.x1 + (size_t)row * a.D + c) = make_float2(xv[p][0], xv[p][1]);
+        }
+        LnStats s2 = row_stats<NP>(xv, a.D, a.eps);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float y0 = (xv[p][0] - s2.mean) * s2.rstd * a.g2[c] + a.b2[c];
+            float y1 = (xv[p][1] - s2.mean) * s2.rstd * a.g2[c + 1] + a.b2[c + 1];
+            *reinterpret_cast<uint32_t*>(a.xn + (size_t)row * a.D + c) = pack_bf16(y0, y1);
+        }
+        if (lane == 0) {
+            a.st1[2 * row] = s1.mean; a.st1[2 * row + 1] = s1.rstd;
+            a.st2[2 * row] = s2.mean; a.st2[2 * row + 1] = s2.rstd;
+        }
+    }
+}
+
+// backward of the above.  dy: grad of the layer output (flows through the FFN residual), dxn: grad of LN2 output.
+struct LnGateBwdArgs {
+    const float* dy; const float* dxn;
+    const float* x1; const float* st1; const float* st2;
+    const bf16* O; int ldo;
+    const bf16* U; int ldu;
+    const bf16* zu; int ldz;       // pre-activation of U (for silu')
+    const float *g1, *b1, *g2;
+    float* dx1;                    // [T,D] fp32
+    bf16* dO; int lddo;            // [T,D]
+    bf16* dzu; int lddz;           // [T, ...] grad wrt U pre-activation
+    float *dg1, *db1, *dg2, *db2;  // accumulated (atomicAdd)
+    int T, D;
+    Dropout drop;
+};
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs a) {
+    a.drop.resolve();
+    __shared__ float red[4][ROW_THREADS / 32][64 * NP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    float adg1[NP][2], adb1[NP][2], adg2[NP][2], adb2[NP][2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) adg1[p][e] = adb1[p][e] = adg2[p][e] = adb2[p][e] = 0.f;
+    const float invD = 1.f / (float)a.D;
+
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        const float m1 = a.st1[2 * row], r1 = a.st1[2 * row + 1], m2 = a.st2[2 * row], r2 = a.st2[2 * row + 1];
+        float xh2[NP][2], gg[NP][2], dx1[NP][2];
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float2 xv = *reinterpret_cast<const float2*>(a.x1 + (size_t)row * a.D + c);
+            float2 dn = *reinterpret_cast<const float2*>(a.dxn + (size_t)row * a.D + c);
+            xh2[p][0] = (xv.x - m2) * r2; xh2[p][1] = (xv.y - m2) * r2;
+            adg2[p][0] += dn.x * xh2[p][0]; adg2[p][1] += dn.y * xh2[p][1];
+            adb2[p][0] += dn.x; adb2[p][1] += dn.y;
+            gg[p][0] = dn.x * a.g2[c]; gg[p][1] = dn.y * a.g2[c + 1];
+            sa += gg[p][0] + gg[p][1];
+            sb += gg[p][0] * xh2[p][0] + gg[p][1] * xh2[p][1];
+        }
+        sa = warp_sum(sa) * invD; sb = warp_sum(sb) * invD;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float2 dyv = *reinterpret_cast<const float2*>(a.dy + (size_t)row * a.D + c);
+            dx1[p][0] = dyv.x + r2 * (gg[p][0] - sa - xh2[p][0] * sb);
+            dx1[p][1] = dyv.y + r2 * (gg[p][1] - sa - xh2[p][1] * sb);
+            *reinterpret_cast<float2*>(a.dx1 + (size_t)row * a.D + c) = make_float2(dx1[p][0], dx1[p][1]);
+        }
+        // gate + LN1
+        float xh1[NP][2], gn[NP][2];
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float2 ov = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.O + (size_t)row * a.ldo + c));
+            float2 uv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.U + (size_t)row * a.ldu + c));
+            float2 zv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.zu + (size_t)row * a.ldz + c));
+            float o2[2] = {ov.x, ov.y}, u2[2] = {uv.x, uv.y}, z2[2] = {zv.x, zv.y}, dzu[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float dG = a.drop.apply(dx1[p][e], (size_t)row * a.D + c + e);
+                xh1[p][e] = (o2[e] - m1) * r1;
+                float n = xh1[p][e] * a.g1[c + e] + a.b1[c + e];
+                dzu[e] = dG * n * dsiluf(z2[e]);
+                float dN = dG * u2[e];
+                adg1[p][e] += dN * xh1[p][e];
+                adb1[p][e] += dN;
+                gn[p][e] = dN * a.g1[c + e];
+                ta += gn[p][e];
+                tb += gn[p][e] * xh1[p][e];
+            }
+            *reinterpret_cast<uint32_t*>(a.dzu + (size_t)row * a.lddz + c) = pack_bf16(dzu[0], dzu[1]);
+        }
+        ta = warp_sum(ta) * invD; tb = warp_sum(tb) * invD;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float d0 = r1 * (gn[p][0] - ta - xh1[p][0] * tb), d1 = r1 * (gn[p][1] - ta - xh1[p][1] * tb);
+            *reinterpret_cast<uint32_t*>(a.dO + (size_t)row * a.lddo + c) = pack_bf16(d0, d1);
+        }
+    }
+    // CTA reduction of the four parameter-gradient vectors, then one atomicAdd per column per CTA
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = 2 * lane + 64 * p + e;
+            red[0][wib][c] = adg1[p][e]; red[1][wib][c] = adb1[p][e];
+            red[2][wib][c] = adg2[p][e]; red[3][wib][c] = adb2[p][e];
+        }
+    __syncthreads();
+    float* outs[4] = {a.dg1, a.db1, a.dg2, a.db2};
+    for (int i = threadIdx.x; i < 4 * a.D; i += ROW_THREADS) {
+        int which = i / a.D, c = i % a.D;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[which][w][c];
+        atomicAdd(outs[which] + c, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plain LayerNorm fwd / bwd
+// y = LN(x) (fp32 in) -> bf16 and/or fp32 out, stats saved.
+struct LnFwdArgs {
+    const float* x; const float *g, *b;
+    bf16* y_bf16; float* y_f32;  // either nullable
+    float* st;
+    int T, D; float eps;
+};
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(LnFwdArgs a) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        float xv[NP][2];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float2 f = *reinterpret_cast<const float2*>(a.x + (size_t)row * a.D + 2 * lane + 64 * p);
+            xv[p][0] = f.x; xv[p][1] = f.y;
+        }
+        LnStats s = row_stats<NP>(xv, a.D, a.eps);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float y0 = (xv[p][0] - s.mean) * s.rstd * a.g[c] + a.b[c];
+            float y1 = (xv[p][1] - s.mean) * s.rstd * a.g[c + 1] + a.b[c + 1];
+            if (a.y_bf16) *reinterpret_cast<uint32_t*>(a.y_bf16 + (size_t)row * a.D + c) = pack_bf16(y0, y1);
+            if (a.y_f32) *reinterpret_cast<float2*>(a.y_f32 + (size_t)row * a.D + c) = make_float2(y0, y1);
+        }
+        if (lane == 0 && a.st) { a.st[2 * row] = s.mean; a.st[2 * row + 1] = s.rstd; }
+    }
+}
+// dx = (res ? res : 0) + LNbwd(dy) ; dg += , db +=
+struct LnBwdArgs {
+    const float* dy; const float* x; const float* st; const float* g;
+    const float* res;  // nullable, added to dx
+    float* dx; float *dg, *db;
+    int T, D;
+};
+template <int NP>
+__global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a) {
+    __shared__ float red[2][ROW_THREADS / 32][64 * NP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    float adg[NP][2], adb[NP][2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) adg[p][0] = adg[p][1] = adb[p][0] = adb[p][1] = 0.f;
+    const float invD = 1.f / (float)a.D;
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        const float m = a.st[2 * row], r = a.st[2 * row + 1];
+        float xh[NP][2], gg[NP][2];
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float2 xv = *reinterpret_cast<const float2*>(a.x + (size_t)row * a.D + c);
+            float2 dv = *reinterpret_cast<const float2*>(a.dy + (size_t)row * a.D + c);
+            xh[p][0] = (xv.x - m) * r; xh[p][1] = (xv.y - m) * r;
+            adg[p][0] += dv.x * xh[p][0]; adg[p][1] += dv.y * xh[p][1];
+            adb[p][0] += dv.x; adb[p][1] += dv.y;
+            gg[p][0] = dv.x * a.g[c]; gg[p][1] = dv.y * a.g[c + 1];
+            sa += gg[p][0] + gg[p][1];
+            sb += gg[p][0] * xh[p][0] + gg[p][1] * xh[p][1];
+        }
+        sa = warp_sum(sa) * invD; sb = warp_sum(sb) * invD;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int c = 2 * lane + 64 * p;
+            float d0 = r * (gg[p][0] - sa - xh[p][0] * sb), d1 = r * (gg[p][1] - sa - xh[p][1] * sb);
+            if (a.res) {
+                float2 rv = *reinterpret_cast<const float2*>(a.res + (size_t)row * a.D + c);
+                d0 += rv.x; d1 += rv.y;
+            }
+            *reinterpret_cast<float2*>(a.dx + (size_t)row * a.D + c) = make_float2(d0, d1);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = 2 * lane + 64 * p + e;
+            red[0][wib][c] = adg[p][e]; red[1][wib][c] = adb[p][e];
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.D; i += ROW_THREADS) {
+        int which = i / a.D, c = i % a.D;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[which][w][c];
+        atomicAdd((which ? a.db : a.dg) + c, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ casts / column sums
+// out_bf16[i] = bf16(dropmask(in[i]) * row_scale[row])       (n = T*D elements, D = row length)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n, int D, Dropout drop,
+                                     const float* __restrict__ row_scale) {
+    drop.resolve();
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 v = *reinterpret_cast<const float4*>(in + i);
+        float rs = row_scale ? row_scale[i / D] : 1.f;
+        uint2 o;
+        o.x = pack_bf16(drop.apply(v.x, i) * rs, drop.apply(v.y, i + 1) * rs);
+        o.y = pack_bf16(drop.apply(v.z, i + 2) * rs, drop.apply(v.w, i + 3) * rs);
+        *reinterpret_cast<uint2*>(out + i) = o;
+    }
+}
+// out[c] += sum_r in[r, c]   in: bf16 [T, ld], columns [0, N) ; grid (ceil(N/64), chunks) ; block 256 = 32 col-pairs x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ in, int T, int N, int ld, float* __restrict__ out) {
+    __shared__ float red[8][64];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + 2 * tx;
+    const int rows_per = (T + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(T, r0 + rows_per);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < N) {
+        for (int r = r0 + ty; r < r1; r += 8) {
+            float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (size_t)r * ld + c));
+            s0 += v.x; s1 += v.y;
+        }
+    }
+    red[ty][2 * tx] = s0; red[ty][2 * tx + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        int cc = blockIdx.x * 64 + threadIdx.x;
+        if (cc < N) atomicAdd(out + cc, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// x[t,:] = drop(E[ids[t],:] * scale (+ pos[t % L,:]))  -> fp32 ; pad[t] = ids[t]==0   (hstu.py:124-128 ; sasrec.py:100-111)
+struct EmbedArgs {
+    const long long* ids; const float* E; const float* pos;  // pos nullable [>=L, D]
+    float* x; uint8_t* pad;
+    int T, L, D; float scale; int mask_pad_rows;  // sasrec: x *= (id != 0)
+    Dropout drop;
+};
+__global__ void __launch_bounds__(ROW_THREADS) embed_fwd_kernel(EmbedArgs a) {
+    a.drop.resolve();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        long long id = a.ids[row];
+        if (lane == 0 && a.pad) a.pad[row] = id == 0;
+        const float* src = a.E + (size_t)id * a.D;
+        const float* ps = a.pos ? a.pos + (size_t)(row % a.L) * a.D : nullptr;
+        const float keep = (a.mask_pad_rows && id == 0) ? 0.f : 1.f;
+        for (int c = lane * 4; c < a.D; c += 128) {
+            float4 v = *reinterpret_cast<const float4*>(src + c);
+            float e[4] = {v.x * a.scale, v.y * a.scale, v.z * a.scale, v.w * a.scale};
+            if (ps) {
+                float4 p = *reinterpret_cast<const float4*>(ps + c);
+                e[0] += p.x; e[1] += p.y; e[2] += p.z; e[3] += p.w;
+            }
+            size_t o = (size_t)row * a.D + c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = a.drop.apply(e[k], o + k) * keep;
+            *reinterpret_cast<float4*>(a.x + o) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+}
+// dE[ids[t],:] += scale * dropmask(dx[t,:]) for ids[t] != 0 (padding_idx) ; dpos[t % L,:] += dropmask(dx[t,:])
+struct EmbedBwdArgs {
+    const long long* ids; const float* dx; float* dE; float* dpos;
+    int T, L, D; float scale; int mask_pad_rows;
+    Dropout drop;
+};
+__global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) {
+    a.drop.resolve();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = gridDim.x * (ROW_THREADS / 32);
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
+        long long id = a.ids[row];
+        if (id == 0 && (a.mask_pad_rows || !a.dpos)) continue;
+        for (int c = lane; c < a.D; c += 32) {
+            size_t o = (size_t)row * a.D + c;
+            float gvl = a.drop.apply(a.dx[o], o);
+            if (id != 0) atomicAdd(a.dE + (size_t)id * a.D + c, gvl * a.scale);
+            if (a.dpos && !(a.mask_pad_rows && id == 0)) atomicAdd(a.dpos + (size_t)(row % a.L) * a.D + c, gvl);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cross entropy on bf16 logits
+// count = #(targets != 0)  -> inv_count (0 if none)
+__global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* __restrict__ inv_count, float* __restrict__ loss) {
+    __shared__ int red[32];
+    int c = 0;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        *inv_count = s > 0 ? 1.f / (float)s : 0.f;
+        *loss = 0.f;
+    }
+}
+// one CTA per row: loss += (lse - logit[target]) * inv_count ; logits <- (softmax - onehot) * inv_count  (0 for ignored rows)
+// pad columns [C, ld) are written with zeros.   (hstu.py:141-146, ignore_index = 0, class 0 stays in the denominator)
+__global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ tg,
+                                                        const float* __restrict__ inv_count, float* __restrict__ loss,
+                                                        int write_grad) {
+    __shared__ float red[8];
+    __shared__ float bc[2];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    bf16* lr = logits + (size_t)row * ld;
+    const long long t = tg[row];
+    const float ic = *inv_count;
+    if (t == 0) {
+        if (write_grad)
+            for (int c = tid; c < ld; c += 256) lr[c] = __float2bfloat16(0.f);
+        return;
+    }
+    float m = -INFINITY;
+    for (int c = tid; c < C; c += 256) m = fmaxf(m, __bfloat162float(lr[c]));
+    m = warp_max(m);
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float mm = red[0];
+        for (int w = 1; w < 8; ++w) mm = fmaxf(mm, red[w]);
+        bc[0] = mm;
+    }
+    __syncthreads();
+    m = bc[0];
+    float s = 0.f;
+    for (int c = tid; c < C; c += 256) s += __expf(__bfloat162float(lr[c]) - m);
+    s = warp_sum(s);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float ss = 0.f;
+        for (int w = 0; w < 8; ++w) ss += red[w];
+        bc[1] = ss;
+        float lse = m + logf(ss);
+        atomicAdd(loss, (lse - __bfloat162float(lr[t])) * ic);
+    }
+    __syncthreads();
+    if (!write_grad) return;
+    const float inv_s = 1.f / bc[1];
+    for (int c = tid; c < ld; c += 256) {
+        float gvl = 0.f;
+        if (c < C) {
+            gvl = __expf(__bfloat162float(lr[c]) - m) * inv_s;
+            if (c == (int)t) gvl -= 1.f;
+            gvl *= ic;
+        }
+        lr[c] = __float2bfloat16(gvl);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused Adam (torch.optim.Adam semantics)
+// state[0] = step (as float), state[1] = 1 - beta1^step, state[2] = 1 - beta2^step ; ticked on device so a CUDA graph replays correctly
+__global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
+    float step = state[0] + 1.f;
+    state[0] = step;
+    state[1] = 1.f - powf(beta1, step);
+    state[2] = 1.f - powf(beta2, step);
+}
+struct AdamArgs {
+    float* p; float* g; float* m; float* v; bf16* p_bf16;  // p_bf16 nullable
+    size_t n;
+    const float* state;
+    float lr, beta1, beta2, eps, weight_decay, grad_scale;
+    int zero_grad;
+};
+__global__ void adam_step_kernel(AdamArgs a) {
+    const float bc1 = a.state[1], bc2 = a.state[2];
+    const float step_size = a.lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < a.n; i += stride) {
+        float p = a.p[i], g = a.g[i] * a.grad_scale;
+        if (a.weight_decay != 0.f) g += a.weight_decay * p;
+        float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+        float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+        a.m[i] = m;
+        a.v[i] = v;
+        float denom = sqrtf(v) * inv_sqrt_bc2 + a.eps;
+        p -= step_size * (m / denom);
+        a.p[i] = p;
+        if (a.p_bf16) a.p_bf16[i] = __float2bfloat16(p);
+        if (a.zero_grad) a.g[i] = 0.f;
+    }
+}
+__global__ void cast_flat_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
+}
+
+}  // namespace grb

@@ -1,0 +1,333 @@
+"""torch-facing wrappers of the C ABI: tensors in, tensors out, autograd wired by hand.
+
+Every function here hands raw device pointers + the current CUDA stream to ``libgenrec_b200.so`` (ctypes, see
+``_lib.py``); PyTorch only provides memory, streams and the autograd graph.  CPU tensors raise - there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HstuDims, HstuLayerGrads, HstuLayerParams, HstuSeq, SasrecDims, check, ptr, require_cuda, stream_ptr
+
+PARAM_ORDER = ("proj_w", "proj_b", "pos_table", "time_table", "ln1_g", "ln1_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b",
+               "ln2_g", "ln2_b")
+BF16_PARAMS = ("proj_w", "ffn1_w", "ffn2_w")
+
+
+def _u8(n, device):
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 -> bf16 copy with our own kernel (weights mirror)."""
+    require_cuda(src)
+    src = src.detach().contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(_lib.load().grb_cast_f32_to_bf16(ptr(src), ptr(out), src.numel(), stream_ptr(src.device)))
+    _lib.count_launches(1)
+    return out
+
+
+class SeqMeta:
+    """Per-batch sequence metadata shared by all layers of one forward: pad flags, timestamps, bucket tables."""
+
+    def __init__(self, pad_u8: torch.Tensor, timestamps: Optional[torch.Tensor], pos_bucket: torch.Tensor,
+                 time_thr: torch.Tensor):
+        self.pad = pad_u8
+        self.timestamps = timestamps
+        self.pos_bucket = pos_bucket
+        self.time_thr = time_thr
+
+    def struct(self) -> HstuSeq:
+        return HstuSeq(ptr(self.pad), ptr(self.timestamps), ptr(self.pos_bucket), ptr(self.time_thr))
+
+
+def _dims(B, L, D, H, npos, ntime, p, seed, seed_dev, layer) -> HstuDims:
+    return HstuDims(B, L, D, H, npos, ntime, float(p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), layer)
+
+
+class HstuLayerFn(torch.autograd.Function):
+    """One HSTU block.  forward = grb_hstu_layer_forward, backward = grb_hstu_layer_backward."""
+
+    @staticmethod
+    def forward(ctx, x, meta: SeqMeta, cfg: dict, bf16w: dict, *params):
+        # params in PARAM_ORDER (fp32 masters; time_table may be None)
+        lib = _lib.load()
+        require_cuda(x)
+        B, L, D = x.shape
+        xc = x.detach().contiguous().float()
+        named = dict(zip(PARAM_ORDER, params))
+        has_time = named["time_table"] is not None and meta.timestamps is not None
+        dims = _dims(B, L, D, cfg["H"], cfg["npos"], cfg["ntime"] if has_time else 0, cfg["p"], cfg["seed"], cfg["seed_dev"],
+                     cfg["layer"])
+        pstruct = HstuLayerParams(*[
+            ptr(bf16w[n]) if n in BF16_PARAMS else (ptr(named[n].detach()) if named[n] is not None and (n != "time_table" or has_time) else None)
+            for n in PARAM_ORDER])
+        nbytes = lib.grb_hstu_layer_saved_bytes(C.byref(dims))
+        if nbytes == 0:
+            raise _lib.GrbError(lib.grb_last_error().decode())
+        saved = _u8(nbytes, x.device)
+        y = torch.empty_like(xc)
+        seq = meta.struct()
+        check(lib.grb_hstu_layer_forward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(xc), ptr(y), ptr(saved),
+                                         stream_ptr(x.device)))
+        _lib.count_launches(6)
+        ctx.meta, ctx.cfg, ctx.bf16w, ctx.has_time = meta, cfg, bf16w, has_time
+        ctx.saved_blob = saved
+        ctx.shape = (B, L, D)
+        ctx.save_for_backward(*[p for p in params if p is not None])
+        ctx.param_present = [p is not None for p in params]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        B, L, D = ctx.shape
+        cfg, meta, has_time = ctx.cfg, ctx.meta, ctx.has_time
+        it = iter(ctx.saved_tensors)
+        params = [next(it) if present else None for present in ctx.param_present]
+        named = dict(zip(PARAM_ORDER, params))
+        dims = _dims(B, L, D, cfg["H"], cfg["npos"], cfg["ntime"] if has_time else 0, cfg["p"], cfg["seed"], cfg["seed_dev"],
+                     cfg["layer"])
+        pstruct = HstuLayerParams(*[
+            ptr(ctx.bf16w[n]) if n in BF16_PARAMS else (ptr(named[n].detach()) if named[n] is not None and (n != "time_table" or has_time) else None)
+            for n in PARAM_ORDER])
+        sink = cfg.get("grad_sink")
+        if sink is not None:      # accumulate straight into the flat gradient buffer (genrec_b200.optim.FlatAdam)
+            grads = {n: (sink[n] if named[n] is not None else None) for n in PARAM_ORDER}
+        else:
+            grads = {n: (torch.zeros_like(named[n], dtype=torch.float32) if named[n] is not None else None) for n in PARAM_ORDER}
+        gstruct = HstuLayerGrads(*[ptr(grads[n]) for n in PARAM_ORDER])
+        dyc = dy.contiguous().float()
+        dx = torch.empty_like(dyc)
+        ws = _u8(lib.grb_hstu_layer_workspace_bytes(C.byref(dims)), dy.device)
+        seq = meta.struct()
+        check(lib.grb_hstu_layer_backward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(dyc), ptr(ctx.saved_blob), ptr(dx),
+                                          C.byref(gstruct), ptr(ws), stream_ptr(dy.device)))
+        _lib.count_launches(15)
+        ctx.saved_blob = None
+        if sink is not None:
+            return (dx, None, None, None, *([None] * len(PARAM_ORDER)))
+        return (dx, None, None, None, *[grads[n] for n in PARAM_ORDER])
+
+
+class EmbedFn(torch.autograd.Function):
+    """x = dropout(E[ids] * scale (+ pos)) ; also emits the uint8 pad flags."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pos_table, scale, mask_pad_rows, p, seed, seed_dev, sink=None):
+        lib = _lib.load()
+        require_cuda(ids, table)
+        ctx.sink = sink
+        B, L = ids.shape
+        D = table.shape[1]
+        ids = ids.contiguous()
+        x = torch.empty(B, L, D, dtype=torch.float32, device=ids.device)
+        pad = torch.empty(B, L, dtype=torch.uint8, device=ids.device)
+        check(lib.grb_embed_forward(ptr(ids), ptr(table.detach()), ptr(pos_table.detach()) if pos_table is not None else None,
+                                    ptr(x), ptr(pad), B, L, D, float(scale), int(mask_pad_rows), float(p), int(seed), ptr(seed_dev),
+                                    stream_ptr(ids.device)))
+        _lib.count_launches(1)
+        ctx.save_for_backward(ids)
+        ctx.args = (table.shape, None if pos_table is None else pos_table.shape, scale, mask_pad_rows, p, seed, seed_dev)
+        ctx.mark_non_differentiable(pad)
+        return x, pad
+
+    @staticmethod
+    def backward(ctx, dx, _dpad):
+        lib = _lib.load()
+        (ids,) = ctx.saved_tensors
+        tshape, pshape, scale, mask_pad_rows, p, seed, seed_dev = ctx.args
+        B, L = ids.shape
+        D = tshape[1]
+        dx = dx.contiguous().float()
+        if ctx.sink is not None:
+            dtable, dpos = ctx.sink
+        else:
+            dtable = torch.zeros(tshape, dtype=torch.float32, device=dx.device)
+            dpos = torch.zeros(pshape, dtype=torch.float32, device=dx.device) if pshape is not None else None
+        check(lib.grb_embed_backward(ptr(ids), ptr(dx), ptr(dtable), ptr(dpos), B, L, D, float(scale), int(mask_pad_rows), float(p),
+                                     int(seed), ptr(seed_dev), stream_ptr(dx.device)))
+        _lib.count_launches(1)
+        if ctx.sink is not None:
+            return (None,) * 9
+        return None, dtable, dpos, None, None, None, None, None, None
+
+
+class HeadLossFn(torch.autograd.Function):
+    """loss = CE(LN(x) @ E^T, targets, ignore_index=0); gradients are produced in the same pass (the loss is a scalar,
+    so backward only rescales them by the incoming grad)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_g, ln_b, table, table_bf16, targets, eps, sink=None):
+        """sink = (dln_g, dln_b, dtable) views of the flat gradient buffer: parameter gradients are accumulated there
+        during this call, ASSUMING the loss is back-propagated exactly once with gradient 1 (FlatAdam contract)."""
+        lib = _lib.load()
+        ctx.sink = sink
+        require_cuda(x, table, targets)
+        B, L, D = x.shape
+        T, Cn = B * L, table.shape[0]
+        xc = x.detach().contiguous().float()
+        tg = targets.contiguous()
+        need_grad = any(ctx.needs_input_grad[:4])
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        ws = _u8(lib.grb_head_workspace_bytes(T, D, Cn), x.device)
+        if need_grad and sink is not None:
+            dx = torch.empty_like(xc)
+            dg, db, dtable = sink
+        elif need_grad:
+            dx = torch.empty_like(xc)
+            dtable = torch.zeros(table.shape, dtype=torch.float32, device=x.device)
+            dg = torch.zeros_like(ln_g, dtype=torch.float32)
+            db = torch.zeros_like(ln_b, dtype=torch.float32)
+        else:
+            dx = dtable = dg = db = None
+        check(lib.grb_head_loss_forward_backward(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), ptr(tg),
+                                                 T, D, Cn, ptr(loss), ptr(dx), ptr(dtable), ptr(dg), ptr(db), ptr(ws),
+                                                 stream_ptr(x.device)))
+        _lib.count_launches(8 if need_grad else 4)
+        ctx.grads = (dx, dg, db, dtable)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dx, dg, db, dtable = ctx.grads
+        ctx.grads = None
+        if dx is None:
+            return (None,) * 8
+        if ctx.sink is not None:
+            return dx, None, None, None, None, None, None, None
+        return dx * dloss, dg * dloss, db * dloss, dtable * dloss, None, None, None, None
+
+
+def head_logits(x, ln_g, ln_b, table, table_bf16, eps) -> torch.Tensor:
+    """fp32 logits [B, L, C] (no autograd - inference / API parity path)."""
+    lib = _lib.load()
+    require_cuda(x, table)
+    B, L, D = x.shape
+    T, Cn = B * L, table.shape[0]
+    xc = x.detach().contiguous().float()
+    logits = torch.empty(B, L, Cn, dtype=torch.float32, device=x.device)
+    ws = _u8(lib.grb_head_workspace_bytes(T, D, Cn), x.device)
+    check(lib.grb_head_logits(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), T, D, Cn, ptr(logits), ptr(ws),
+                              stream_ptr(x.device)))
+    _lib.count_launches(2)
+    return logits
+
+
+# ------------------------------------------------------------------------------------------------ SASRec pieces
+def layernorm_fwd(x, g, b, eps, want_bf16=True, want_f32=False):
+    lib = _lib.load()
+    T, D = x.numel() // x.shape[-1], x.shape[-1]
+    yb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    yf = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    st = torch.empty(T, 2, dtype=torch.float32, device=x.device)
+    check(lib.grb_layernorm_forward(ptr(x), ptr(g), ptr(b), float(eps), T, D, ptr(yb), ptr(yf), ptr(st), stream_ptr(x.device)))
+    _lib.count_launches(1)
+    return yb, yf, st
+
+
+def layernorm_bwd(dy, x, st, g, residual=None):
+    lib = _lib.load()
+    T, D = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = torch.zeros_like(g)
+    db = torch.zeros_like(g)
+    check(lib.grb_layernorm_backward(ptr(dy), ptr(x), ptr(st), ptr(g), ptr(residual), T, D, ptr(dx), ptr(dg), ptr(db), stream_ptr(x.device)))
+    _lib.count_launches(1)
+    return dx, dg, db
+
+
+def linear_fwd(xb, wb, bias, act, p=0.0, seed=0, seed_dev=None, site=0):
+    """z = xb @ wb^T + bias (bf16) ; act: 0 none, 1 silu, 2 relu -> returns (z, act(z) with dropout)"""
+    lib = _lib.load()
+    T, K = xb.numel() // xb.shape[-1], xb.shape[-1]
+    N = wb.shape[0]
+    z = torch.empty(*xb.shape[:-1], N, dtype=torch.bfloat16, device=xb.device)
+    a = torch.empty_like(z) if act else None
+    check(lib.grb_linear_forward(ptr(xb), ptr(wb), ptr(bias), T, N, K, act, ptr(z), ptr(a), float(p), int(seed), ptr(seed_dev), site,
+                                 stream_ptr(xb.device)))
+    _lib.count_launches(1)
+    return z, a
+
+
+def linear_residual_fwd(xb, wb, bias, residual, row_scale=None, p=0.0, seed=0, seed_dev=None, site=0):
+    lib = _lib.load()
+    T, K = xb.numel() // xb.shape[-1], xb.shape[-1]
+    N = wb.shape[0]
+    y = torch.empty(*xb.shape[:-1], N, dtype=torch.float32, device=xb.device)
+    check(lib.grb_linear_residual_forward(ptr(xb), ptr(wb), ptr(bias), ptr(residual), ptr(row_scale), T, N, K, ptr(y), float(p), int(seed),
+                                          ptr(seed_dev), site, stream_ptr(xb.device)))
+    _lib.count_launches(1)
+    return y
+
+
+def linear_bwd(dyb, wb, xb, need_dx=True, dx_residual=None, need_dw=True):
+    """dyb [T,N] bf16 ; wb [N,K] bf16 ; xb [T,K] bf16 -> dx fp32 [T,K] (+ residual), dw fp32 [N,K], db fp32 [N]"""
+    lib = _lib.load()
+    N, K = wb.shape
+    T = dyb.numel() // N
+    dx = torch.empty(*dyb.shape[:-1], K, dtype=torch.float32, device=dyb.device) if need_dx else None
+    dw = torch.zeros(N, K, dtype=torch.float32, device=dyb.device) if need_dw else None
+    db = torch.zeros(N, dtype=torch.float32, device=dyb.device) if need_dw else None
+    check(lib.grb_linear_backward(ptr(dyb), ptr(wb), ptr(xb), T, N, K, ptr(dx), ptr(dx_residual), ptr(dw), ptr(db), stream_ptr(dyb.device)))
+    _lib.count_launches(3)
+    return dx, dw, db
+
+
+def sasrec_attention_fwd(q, k, v, pad, H, p=0.0, seed=0, seed_dev=None, layer=0):
+    lib = _lib.load()
+    B, L, D = q.shape
+    dims = SasrecDims(B, L, D, H, float(p), int(seed), ptr(seed_dev), layer)
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, L, dtype=torch.float32, device=q.device)
+    check(lib.grb_sasrec_attention_forward(C.byref(dims), ptr(q), ptr(k), ptr(v), ptr(pad), ptr(out), ptr(lse), stream_ptr(q.device)))
+    _lib.count_launches(1)
+    return out, lse
+
+
+def sasrec_attention_bwd(q, k, v, pad, out, lse, dout, H, p=0.0, seed=0, seed_dev=None, layer=0):
+    lib = _lib.load()
+    B, L, D = q.shape
+    dims = SasrecDims(B, L, D, H, float(p), int(seed), ptr(seed_dev), layer)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    check(lib.grb_sasrec_attention_backward(C.byref(dims), ptr(q), ptr(k), ptr(v), ptr(pad), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk),
+                                            ptr(dv), stream_ptr(q.device)))
+    _lib.count_launches(2)
+    return dq, dk, dv
+
+
+def dact_(g_bf16, z_bf16, act):
+    check(_lib.load().grb_dact(ptr(g_bf16), ptr(z_bf16), g_bf16.numel(), act, stream_ptr(g_bf16.device)))
+    _lib.count_launches(1)
+    return g_bf16
+
+
+# ------------------------------------------------------------------------------------------------ RQ-VAE
+def rq_residual_argmin(x: torch.Tensor, codebooks: torch.Tensor, commitment: float = 0.25, want_aux: bool = True):
+    """x [N, D] fp32, codebooks [levels, K, D] fp32 -> ids [N, levels] int64 (+ emb, res [N, D, levels], loss [N])."""
+    lib = _lib.load()
+    require_cuda(x, codebooks)
+    x = x.detach().contiguous().float()
+    cb = codebooks.detach().contiguous().float()
+    N, D = x.shape
+    levels, K, _ = cb.shape
+    ids = torch.empty(N, levels, dtype=torch.int64, device=x.device)
+    emb = torch.empty(N, D, levels, dtype=torch.float32, device=x.device) if want_aux else None
+    res = torch.empty(N, D, levels, dtype=torch.float32, device=x.device) if want_aux else None
+    loss = torch.empty(N, dtype=torch.float32, device=x.device) if want_aux else None
+    check(lib.grb_rq_residual_argmin(ptr(x), ptr(cb), N, D, K, levels, float(commitment), ptr(ids), ptr(emb), ptr(res), ptr(loss), None,
+                                     stream_ptr(x.device)))
+    _lib.count_launches(1)
+    return ids, emb, res, loss
+
+
+def adam_step(p, g, m, v, p_bf16, state, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, zero_grad=True):
+    check(_lib.load().grb_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), ptr(state), lr, beta1, beta2, eps, weight_decay,
+                                    grad_scale, int(zero_grad), stream_ptr(p.device)))
+    _lib.count_launches(2)

@@ -1,0 +1,79 @@
+"""Flat-buffer training runtime: fused Adam + bf16 weight mirror + one NCCL all-reduce per step.
+
+``FlatAdam(model)`` re-homes every parameter of the model as a view into ONE contiguous fp32 buffer, gives each a
+``.grad`` view into one flat gradient buffer, and keeps a flat bf16 mirror that the CUDA kernels read as tensor-core
+operands.  Consequences ("distributed communication backend"):
+  * backward kernels accumulate weight gradients straight into the flat buffer (``grad sink``) - no per-parameter
+    AccumulateGrad kernels, no flatten copy before the all-reduce;
+  * data-parallel training = ONE ``all_reduce(SUM)`` over the flat gradient (NCCL over NVLink/NVSwitch), the 1/world
+    scale folded into the fused Adam kernel, which also refreshes the bf16 mirror and zeroes the gradient;
+  * everything is CUDA-graph capturable (Adam's bias correction is ticked on the device).
+Semantics = ``torch.optim.Adam(params, lr, betas, eps, weight_decay)`` followed by ``zero_grad()``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+
+
+class FlatAdam:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True):
+        params = [p for p in model.parameters() if p.requires_grad]
+        assert params, "no trainable parameters"
+        dev = params[0].device
+        assert dev.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
+        self.model, self.lr, self.betas, self.eps, self.weight_decay = model, lr, betas, eps, weight_decay
+        self.group = process_group
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 63) // 64 * 64          # 256-byte aligned slots (bf16 views stay 16-byte aligned)
+        self.n = n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.mirror = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        self.state = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._mirror_view, self._grad_view = {}, {}
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                k = p.numel()
+                self.flat[o:o + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + k].view(p.shape)
+                p.grad = self.grad[o:o + k].view(p.shape)
+                self._mirror_view[id(p)] = self.mirror[o:o + k].view(p.shape)
+                self._grad_view[id(p)] = p.grad
+        Fn.cast_bf16(self.flat, self.mirror)
+        self.params = params
+        # hand the mirror (and, optionally, the gradient sink) to the modules
+        for mod in model.modules():
+            if hasattr(mod, "_bf16_provider"):
+                mod._bf16_provider = self.mirror_of
+            if grad_sink and hasattr(mod, "_grad_sink"):
+                mod._grad_sink = self.grad_of
+
+    def mirror_of(self, p: torch.Tensor) -> torch.Tensor:
+        return self._mirror_view[id(p)]
+
+    def grad_of(self, p: torch.Tensor) -> Optional[torch.Tensor]:
+        return self._grad_view.get(id(p))
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def step(self) -> None:
+        """all-reduce(SUM) -> fused Adam with grad_scale = 1/world -> mirror refresh -> grad zeroed."""
+        w = self.world()
+        if w > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        Fn.adam_step(self.flat, self.grad, self.m, self.v, self.mirror, self.state, self.lr, self.betas[0], self.betas[1],
+                     self.eps, self.weight_decay, 1.0 / w, True)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        pass  # the fused step already zeroed the flat gradient

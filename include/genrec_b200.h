@@ -1,0 +1,155 @@
+/* genrec_b200 - C ABI of the B200-native (sm_100a) hot path of phonism/genrec.
+ *
+ * The reference is pure Python/PyTorch: it has no FFI of its own.  The interface each entry point below replaces is
+ * therefore the body of the reference nn.Module method named in its comment (file:line under /root/reference); the
+ * reference-side binding a maintainer adds is the ctypes stub shown in INTEGRATION.md (and shipped as
+ * genrec_b200/_lib.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host; no torch types cross this boundary;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises, nothing allocates:
+ *     scratch and saved-for-backward storage is caller-provided (sizes from the *_bytes() queries), so every entry
+ *     point is CUDA-graph capturable;
+ *   - return value 0 = success; otherwise a negative GRB_E* code, text via grb_last_error();
+ *   - activations: T = B*L token rows, row-major [T, D]; fp32 residual stream, bf16 tensor-core operands;
+ *   - "bf16" pointers are void* to 2-byte bfloat16 storage;
+ *   - gradient outputs of parameters are ACCUMULATED (+=) so they can point straight into a flat, pre-zeroed grad buffer.
+ */
+#ifndef GENREC_B200_H
+#define GENREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRB_OK 0
+#define GRB_EINVAL (-1)   /* unsupported shape / null pointer / misaligned buffer */
+#define GRB_ECUDA (-2)    /* a CUDA launch or runtime call failed */
+#define GRB_ENODEV (-3)   /* no sm_100 device */
+
+const char* grb_last_error(void);
+int grb_version(void);
+/* 0 when device `ordinal` is compute capability 10.x, GRB_ENODEV otherwise (host call). */
+int grb_check_device(int ordinal);
+
+/* ------------------------------------------------------------------------------------------------ HSTU block
+ * Replaces HSTULayer.forward (genrec/models/hstu.py:222-280) incl. RelativePositionBias.forward (:330-349) and
+ * TemporalBias.forward (:386-409), and their autograd backward. */
+typedef struct {
+    int B, L, D, H;          /* head_dim = D / H must be 32 (16 and 64 also compiled) ; D in {64,128,256} */
+    int npos, ntime;         /* bucket counts of the two bias tables, each <= 64 ; ntime = 0 disables the temporal term */
+    float dropout_p;         /* 0 in eval mode */
+    uint64_t seed;           /* dropout stream ; the mask is a pure function of (seed, layer_index, site, element) */
+    const uint64_t* seed_dev;/* nullable DEVICE counter added to seed at kernel start: bump it per step so that a captured
+                                CUDA graph draws a fresh mask on every replay */
+    int layer_index;
+} grb_hstu_dims;
+
+typedef struct {
+    const void* proj_w;      /* bf16 [4D, D]   layers.i.projection.weight (order U,V,Q,K along rows) */
+    const float* proj_b;     /* [4D] */
+    const float* pos_table;  /* [npos, H]      layers.i.position_bias.relative_attention_bias.weight */
+    const float* time_table; /* [ntime, H] or NULL   layers.i.temporal_bias.temporal_attention_bias.weight */
+    const float* ln1_g;      /* attn_norm */
+    const float* ln1_b;
+    const void* ffn1_w;      /* bf16 [4D, D]   ffn.0.weight */
+    const float* ffn1_b;
+    const void* ffn2_w;      /* bf16 [D, 4D]   ffn.3.weight */
+    const float* ffn2_b;
+    const float* ln2_g;      /* ffn_norm */
+    const float* ln2_b;
+} grb_hstu_layer_params;
+
+typedef struct {             /* fp32, same shapes as the parameters, accumulated */
+    float* proj_w; float* proj_b; float* pos_table; float* time_table;
+    float* ln1_g; float* ln1_b; float* ffn1_w; float* ffn1_b; float* ffn2_w; float* ffn2_b; float* ln2_g; float* ln2_b;
+} grb_hstu_layer_grads;
+
+typedef struct {
+    const uint8_t* pad;         /* [B, L] 1 = padded key (input_ids == 0, hstu.py:124) */
+    const int64_t* timestamps;  /* [B, L] or NULL (hstu.py:251) */
+    const uint8_t* pos_bucket;  /* [L] bucket of delta = i - j >= 0, precomputed by the host from the reference formula */
+    const int64_t* time_thr;    /* [65] thr[k] = smallest |dt| whose reference bucket is >= k ; thr[64] = INT64_MAX */
+} grb_hstu_seq;
+
+size_t grb_hstu_layer_saved_bytes(const grb_hstu_dims* d);
+size_t grb_hstu_layer_workspace_bytes(const grb_hstu_dims* d);
+int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s,
+                           const float* x, float* y, void* saved, void* stream);
+int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s,
+                            const float* dy, const void* saved, float* dx, const grb_hstu_layer_grads* g,
+                            void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ embedding gather
+ * Replaces item_embedding + emb_dropout (hstu.py:124-128) / the scaled item+position embedding of SASRec
+ * (sasrec.py:100-111).  pos_table may be NULL; mask_pad_rows multiplies rows whose id is 0 by zero (SASRec). */
+int grb_embed_forward(const int64_t* ids, const float* table, const float* pos_table, float* x, uint8_t* pad,
+                      int B, int L, int D, float scale, int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                      void* stream);
+int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float* dpos_table, int B, int L, int D,
+                       float scale, int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------ tied-embedding head
+ * Replaces final_norm + `x @ item_embedding.weight.T` + cross_entropy(ignore_index=0) (hstu.py:134-146,
+ * sasrec.py:118-128) and their backward.  C = num_items + 1 classes. */
+size_t grb_head_workspace_bytes(int T, int D, int C);
+/* training: loss (scalar, mean over targets != 0), dx [T,D], and the three parameter gradients (accumulated). */
+int grb_head_loss_forward_backward(const float* x, const float* ln_g, const float* ln_b, float ln_eps,
+                                   const void* table_bf16, const int64_t* targets, int T, int D, int C, float* loss,
+                                   float* dx, float* dtable, float* dln_g, float* dln_b, void* workspace, void* stream);
+/* inference / API parity: logits fp32 [T, C] (contiguous), optional loss. */
+int grb_head_logits(const float* x, const float* ln_g, const float* ln_b, float ln_eps, const void* table_bf16, int T,
+                    int D, int C, float* logits, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ SASRec attention
+ * Replaces MultiHeadAttention.forward (genrec/models/sasrec.py:192-246) after the three projections:
+ *   out = softmax_j(mask(Q K^T * dh^-1/2)) * query_mask @ V     (residual and projections are GEMM epilogues) */
+typedef struct {
+    int B, L, D, H;
+    float dropout_p; uint64_t seed; const uint64_t* seed_dev; int layer_index;
+} grb_sasrec_dims;
+int grb_sasrec_attention_forward(const grb_sasrec_dims* d, const void* q, const void* k, const void* v,
+                                 const uint8_t* pad, void* out, float* lse, void* stream);
+int grb_sasrec_attention_backward(const grb_sasrec_dims* d, const void* q, const void* k, const void* v,
+                                  const uint8_t* pad, const void* out, const float* lse, const void* dout, void* dq,
+                                  void* dk, void* dv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ generic fused linear pieces
+ * (used by the SASRec block and by tests)   act: 0 none, 1 silu, 2 relu */
+int grb_linear_forward(const void* x_bf16, const void* w_bf16, const float* bias, int T, int N, int K, int act,
+                       void* z_bf16, void* act_bf16, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                       void* stream);
+int grb_linear_residual_forward(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual,
+                                const float* row_scale, int T, int N, int K, float* y, float dropout_p, uint64_t seed,
+                                const uint64_t* seed_dev, uint32_t site, void* stream);
+/* dx[T,K] (+res) = dy[T,N] @ W[N,K] ; dW[N,K] += dy^T x ; db[N] += colsum(dy) */
+int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_bf16, int T, int N, int K,
+                        float* dx_f32, const float* dx_residual, float* dw, float* db, void* stream);
+int grb_dact(const void* g_bf16_in_out, const void* z_bf16, size_t n, int act, void* stream);
+int grb_layernorm_forward(const float* x, const float* g, const float* b, float eps, int T, int D, void* y_bf16,
+                          float* y_f32, float* stats, void* stream);
+int grb_layernorm_backward(const float* dy, const float* x, const float* stats, const float* g, const float* residual,
+                           int T, int D, float* dx, float* dg, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ optimizer / casts */
+int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
+/* torch.optim.Adam semantics on a flat buffer; state = 3 floats {step, 1-b1^step, 1-b2^step} ticked ON DEVICE. */
+int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n, float* state, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ RQ-VAE residual argmin
+ * Replaces the Quantize.forward distance+argmin (genrec/models/rqvae.py:185-199, eval branch :246-248) iterated by
+ * RqVae.get_semantic_ids (:397-412).  x [N, D] fp32 latent, codebooks [levels, K, D] fp32.
+ * ids [N, levels] int64 ; optional emb / res [N, D, levels] (reference layout), loss [N], res_out [N, D]. */
+int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, int D, int K, int levels,
+                           float commitment, int64_t* ids, float* emb, float* res, float* loss, float* res_out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENREC_B200_H */

@@ -65,9 +65,15 @@ def golden_hstu(name, V, D, H, blocks, B, L, seed, use_time=True, pass_ts=True):
     logits, loss = m(ids, ts if pass_ts else None, tg)
     loss.backward()
     grads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in m.named_parameters()}
+    m.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):       # yardstick: the reference's own bf16-autocast error
+        logits_ac, loss_ac = m(ids, ts if pass_ts else None, tg)
+    loss_ac.float().backward()
+    grads_ac = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in m.named_parameters()}
     m.eval()
     top = m.predict(ids, ts if pass_ts else None, top_k=10)
-    torch.save(dict(cfg=dict(num_items=V, embed_dim=D, num_heads=H, num_blocks=blocks, use_temporal_bias=use_time,
+    torch.save(dict(autocast=dict(loss=loss_ac.detach().float(), grads=grads_ac, logits_last=logits_ac.detach().float()[:, -1]),
+                    cfg=dict(num_items=V, embed_dim=D, num_heads=H, num_blocks=blocks, use_temporal_bias=use_time,
                              pass_ts=pass_ts),
                     state_dict={k: v.clone() for k, v in m.state_dict().items()},
                     input_ids=ids, timestamps=ts, targets=tg,
@@ -88,7 +94,16 @@ def golden_hstu_layer(name, D, H, B, L, seed):
     causal = torch.triu(torch.ones(L, L), diagonal=1).bool()
     y = layer(x, causal, ids == 0, ts)
     y.backward(dy)
-    torch.save(dict(cfg=dict(embed_dim=D, num_heads=H),
+    ref = dict(y=y.detach().clone(), dx=x.grad.clone(), grads={n: p.grad.clone() for n, p in layer.named_parameters()})
+    layer.zero_grad(); x.grad = None
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        y_ac = layer(x, causal, ids == 0, ts)
+    y_ac.float().backward(dy)
+    ac = dict(y=y_ac.detach().float(), dx=x.grad.clone(), grads={n: p.grad.clone() for n, p in layer.named_parameters()})
+    layer.zero_grad(); x.grad = None
+    y = layer(x, causal, ids == 0, ts)
+    y.backward(dy)
+    torch.save(dict(autocast=ac, cfg=dict(embed_dim=D, num_heads=H),
                     state_dict={k: v.clone() for k, v in layer.state_dict().items()},
                     x=x.detach(), dy=dy, padding_mask=(ids == 0), timestamps=ts, y=y.detach(), dx=x.grad.clone(),
                     grads={n: p.grad.clone() for n, p in layer.named_parameters()}),
@@ -193,7 +208,7 @@ def main():
     golden_hstu("hstu_model_d128h4_nots.pt", V=40, D=128, H=4, blocks=1, B=3, L=17, seed=20, use_time=True, pass_ts=False)
     golden_hstu("hstu_model_notime.pt", V=40, D=64, H=2, blocks=1, B=3, L=9, seed=30, use_time=False)
     golden_hstu_layer("hstu_layer_d64h2_L70.pt", D=64, H=2, B=3, L=70, seed=40)
-    golden_hstu_layer("hstu_layer_d32h1_L1.pt", D=32, H=1, B=3, L=1, seed=50)
+    golden_hstu_layer("hstu_layer_d64h2_L1.pt", D=64, H=2, B=3, L=1, seed=50)
     golden_sasrec("sasrec_d64h2.pt", V=50, D=64, H=2, blocks=2, F_=256, B=4, L=21, seed=60)
     golden_rqvae("rqvae_3x256x32.pt", seed=70)
     golden_kats("kats.pt")

@@ -1,0 +1,87 @@
+"""Host-side logic of the drop-in modules: state_dict schema, init, bucket tables, thresholds, error behaviour."""
+import pytest
+import torch
+
+from oracle import hstu as oh
+
+
+def test_hstu_state_dict_schema_matches_reference(golden):
+    from genrec_b200.hstu import HSTU
+    for name in ["hstu_model_d64h2.pt", "hstu_model_notime.pt"]:
+        g = golden(name)
+        c = g["cfg"]
+        m = HSTU(c["num_items"], 64, c["embed_dim"], c["num_heads"], c["num_blocks"], use_temporal_bias=c["use_temporal_bias"])
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(g["state_dict"].keys())
+        for k, v in sd.items():
+            assert v.shape == g["state_dict"][k].shape and v.dtype == g["state_dict"][k].dtype, k
+        m.load_state_dict(g["state_dict"])            # strict
+
+
+def test_hstu_init_statistics():
+    from genrec_b200.hstu import HSTU
+    torch.manual_seed(0)
+    m = HSTU(2000, 50, 128, 4, 2)
+    assert m.item_embedding.weight[0].abs().sum() == 0
+    w = m.layers[0].projection.weight
+    assert abs(w.std().item() - 0.02) < 2e-3 and w.abs().max() <= 2.0
+    assert m.layers[0].projection.bias.abs().sum() == 0
+    assert torch.equal(m.final_norm.weight, torch.ones(128))
+    assert sum(p.numel() for p in HSTU(12101, 200, 128, 4, 4).parameters()) == 2_343_936
+
+
+def test_time_thresholds_equal_reference_expression(golden):
+    from genrec_b200.hstu import TemporalBias, time_bucket_thresholds
+    thr = time_bucket_thresholds()
+    assert thr.shape == (65,) and thr[64] == (1 << 63) - 1
+    assert torch.equal(thr[:64], oh.time_bucket_thresholds(64))
+    assert thr[10] == 1023 and thr[11] == 2045          # 0.693 != ln 2
+    k = golden("kats.pt")
+    tb = TemporalBias(64, 2)
+    # the module's stand-alone forward uses the integer thresholds; check it against the reference's fp32-log buckets
+    ts = torch.stack([k["dt"], torch.zeros_like(k["dt"])], 0).T.contiguous()[:4000]      # [N, 2]: dt vs 0
+    bias = tb(ts)                                                                        # [N, H, 2, 2]
+    want = tb.temporal_attention_bias.weight[k["dt_bucket"][:4000].long()]               # [N, H]
+    assert torch.equal(bias[:, :, 0, 1], want)
+    # the device formula: e = floor(log2 d); bucket = e + (d >= thr[e+1])
+    d = k["dt"].clamp(min=1)
+    e = torch.tensor([int(v).bit_length() - 1 for v in d.tolist()])
+    b = (e + (d >= thr[e + 1]).long()).clamp(max=63)
+    assert torch.equal(b.to(torch.int8), k["dt_bucket"])
+
+
+def test_position_bucket_table_is_degenerate_like_the_reference(golden):
+    from genrec_b200.hstu import RelativePositionBias
+    pb = RelativePositionBias(32, 128, 2)
+    t = pb.bucket_of_delta(300, "cpu")
+    assert t.dtype == torch.uint8 and t.shape == (300,) and int(t.max()) == 0
+    k = golden("kats.pt")
+    L = k["rel_bucket_150"].shape[0]
+    pos = torch.arange(L)
+    assert torch.equal(pb._relative_position_bucket(pos[None] - pos[:, None]).to(torch.int8), k["rel_bucket_150"])
+    dense = pb(L, torch.device("cpu"))
+    assert dense.shape == (2, L, L)
+    assert torch.equal(dense, oh.position_bias(pb.relative_attention_bias.weight, L))
+
+
+def test_rqvae_mirror_schema(golden):
+    from genrec_b200.rqvae import RqVae
+    g = golden("rqvae_3x256x32.pt")
+    c = g["cfg"]
+    m = RqVae(c["input_dim"], c["D"], c["hidden_dims"], c["K"], codebook_kmeans_init=False, n_layers=c["levels"], n_cat_features=0)
+    r = m.load_state_dict(g["state_dict"], strict=False)
+    assert not r.unexpected_keys and all(k.startswith("decoder.") for k in r.missing_keys)
+    assert m.codebooks().shape == (3, 256, 32)
+    with pytest.raises(RuntimeError):
+        m.eval().get_semantic_ids(g["x"])       # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        m.train().layers[0](torch.zeros(2, 32), 0.1)
+
+
+def test_genrec_shim_import_paths():
+    import importlib
+    hstu = importlib.import_module("genrec.models.hstu")
+    rq = importlib.import_module("genrec.models.rqvae")
+    import genrec_b200.hstu as ours
+    assert hstu.HSTU is ours.HSTU and hstu.HSTULayer is ours.HSTULayer
+    assert hasattr(rq, "RqVae") and hasattr(rq, "Quantize") and hasattr(rq, "QuantizeForwardMode")

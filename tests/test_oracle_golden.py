@@ -33,7 +33,7 @@ def test_hstu_model_forward_backward(golden, name):
     assert torch.equal(top, g["top10"])
 
 
-@pytest.mark.parametrize("name", ["hstu_layer_d64h2_L70.pt", "hstu_layer_d32h1_L1.pt"])
+@pytest.mark.parametrize("name", ["hstu_layer_d64h2_L70.pt", "hstu_layer_d64h2_L1.pt"])
 def test_hstu_layer(golden, name):
     g = golden(name)
     p = _req(g["state_dict"])
