@@ -205,6 +205,7 @@ def run_ours(args, rank, world, local_rank):
             loss_static = train_step()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    loss_static = None   # drop the eager autograd graph NOW: freeing side-stream blocks while capturing invalidates the capture
     l0 = _lib.launches()
     graph = None
     if not args.no_graph:

@@ -14,6 +14,8 @@
 #include "gemm.cuh"
 #include "rowwise.cuh"
 #include "rq_argmin.cuh"
+#include "tc_gemm.cuh"
+#include <cstdlib>
 
 using namespace grb;
 
@@ -68,6 +70,73 @@ int splitk_for(int M, int N, int K) {
     int kt = (K + GEMM_BK - 1) / GEMM_BK;
     int maxs = kt / 4 > 0 ? kt / 4 : 1;  // at least 4 k-tiles per split
     return want < 1 ? 1 : (want > maxs ? maxs : want);
+}
+
+
+// ---- GEMM dispatch: tcgen05/TMA path (default) or the first-generation mma.sync path (GRB_GEMM=mma, kept as an on-device
+//      cross-check).  Operand majors: *_MN = 0 -> K contiguous, 1 -> M/N contiguous (see tc_gemm.cuh / gemm.cuh).
+bool use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRB_GEMM");
+        v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+int tn_splits(int M, int N, int K) {
+    int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + TC_BN - 1) / TC_BN);
+    int want = (sm_count() + tiles - 1) / tiles;
+    int kb = (K + TC_BK - 1) / TC_BK;
+    int maxs = kb / 2 > 0 ? kb / 2 : 1;
+    return want < 1 ? 1 : (want > maxs ? maxs : want);
+}
+// z = x W^T + b ; act: 0 none, 1 silu, 2 relu   (NT)
+cudaError_t gemm_bias_act(int act, const bf16* x, const bf16* w, const float* bias, bf16* z, bf16* a, int M, int N, int K, const Dropout& drop,
+                          cudaStream_t st) {
+    if (use_tc()) {
+        if (act == 0) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<0>{bias, z, a, N, drop}, sm_count(), st);
+        if (act == 1) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<1>{bias, z, a, N, drop}, sm_count(), st);
+        return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<2>{bias, z, a, N, drop}, sm_count(), st);
+    }
+    if (act == 0) return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasBf16{bias, z, N}, st);
+    if (act == 1) return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasSilu{bias, z, a, N, drop}, st);
+    return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasRelu{bias, z, a, N, drop}, st);
+}
+// y = res + drop(x W^T + b) (* row_scale)   (NT)
+cudaError_t gemm_bias_res(const bf16* x, const bf16* w, const float* bias, const float* res, const float* row_scale, float* y, int M, int N,
+                          int K, const Dropout& drop, cudaStream_t st) {
+    if (use_tc()) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasResidual{bias, res, y, row_scale, N, drop}, sm_count(), st);
+    return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasResidual{bias, res, y, row_scale, N, drop}, st);
+}
+// g[M,N] = dropmask(dy[M,K] W[K,N]) * act'(z)   (NN) ; act 1 silu, 2 relu
+cudaError_t gemm_dact(int act, const bf16* dy, const bf16* w, const bf16* z, bf16* g, int M, int N, int K, const Dropout& drop, cudaStream_t st) {
+    if (use_tc()) {
+        if (act == 1) return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<1>{z, g, N, drop}, sm_count(), st);
+        return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<2>{z, g, N, drop}, sm_count(), st);
+    }
+    if (act == 1) return launch_gemm<0, 1>(dy, w, M, N, K, K, N, 1, EpiDAct<0>{z, g, N, drop}, st);
+    return launch_gemm<0, 1>(dy, w, M, N, K, K, N, 1, EpiDAct<1>{z, g, N, drop}, st);
+}
+// out[M,N] fp32 = scale * A[M,K] B[K,N] (+ res)   (NN)
+cudaError_t gemm_nn_f32(const bf16* A, const bf16* B, float* out, const float* res, float scale, int M, int N, int K, int lda, int ldb,
+                        cudaStream_t st) {
+    if (use_tc()) return launch_tc_gemm<0, 1>(A, B, M, N, K, lda, ldb, 1, TcEpiF32{out, res, N, scale}, sm_count(), st);
+    return launch_gemm<0, 1>(A, B, M, N, K, lda, ldb, 1, EpiF32{out, res, N, scale}, st);
+}
+// out[M,N] fp32 += A^T B with A stored [K,M], B stored [K,N]   (TN, split-K, atomics)
+cudaError_t gemm_tn_atomic(const bf16* A, const bf16* B, float* out, int M, int N, int K, int lda, int ldb, cudaStream_t st) {
+    if (use_tc()) return launch_tc_gemm<1, 1>(A, B, M, N, K, lda, ldb, tn_splits(M, N, K), TcEpiAtomicF32{out, N, 1.f}, sm_count(), st);
+    return launch_gemm<1, 1>(A, B, M, N, K, lda, ldb, splitk_for(M, N, K), EpiAtomicF32{out, N, 1.f}, st);
+}
+// out[M,N] bf16 (leading dim ldo) = A[M,K] B[N,K]^T   (NT)
+cudaError_t gemm_nt_bf16(const bf16* A, const bf16* B, bf16* out, int ldo, int M, int N, int K, cudaStream_t st) {
+    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiBf16{out, ldo}, sm_count(), st);
+    return launch_gemm<0, 0>(A, B, M, N, K, K, K, 1, EpiBf16{out, ldo}, st);
+}
+// out[M,N] fp32 (leading dim N, any parity) = A B^T   (NT)
+cudaError_t gemm_nt_f32_plain(const bf16* A, const bf16* B, float* out, int M, int N, int K, cudaStream_t st) {
+    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiF32Plain{out, N}, sm_count(), st);
+    return launch_gemm<0, 0>(A, B, M, N, K, K, K, 1, EpiF32Scalar{out, N, N}, st);
 }
 
 // ---- carved layouts ------------------------------------------------------------------------------------------
@@ -268,8 +337,7 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
     GRB_TRY(cast_bf16(x, sv.xb, (size_t)T * D, D, nodrop, nullptr, st));
     // 2. P = silu(x Wp^T + bp) -> [U | V | Q | K]                                            (hstu.py:234-235)
     {
-        EpiBiasSilu epi{p->proj_b, sv.zp, sv.P, 4 * D, nodrop};
-        GRB_CUDA((launch_gemm<0, 0>(sv.xb, (const bf16*)p->proj_w, T, 4 * D, D, D, D, 1, epi, st)));
+        GRB_CUDA(gemm_bias_act(1, sv.xb, (const bf16*)p->proj_w, p->proj_b, sv.zp, sv.P, T, 4 * D, D, nodrop, st));
     }
     // 3. O = silu(Q K^T + bias) V, causal + key padding                                      (hstu.py:244-267)
     {
@@ -285,13 +353,13 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
     }
     // 5. h = drop(silu(xn W1^T + b1))                                                        (hstu.py:210-212)
     {
-        EpiBiasSilu epi{p->ffn1_b, sv.z1, sv.hact, 4 * D, make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_HID), d->seed_dev)};
-        GRB_CUDA((launch_gemm<0, 0>(sv.xn, (const bf16*)p->ffn1_w, T, 4 * D, D, D, D, 1, epi, st)));
+        GRB_CUDA(gemm_bias_act(1, sv.xn, (const bf16*)p->ffn1_w, p->ffn1_b, sv.z1, sv.hact, T, 4 * D, D,
+                               make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_HID), d->seed_dev), st));
     }
     // 6. y = x1 + drop(h W2^T + b2)                                                          (hstu.py:213-214, :278)
     {
-        EpiBiasResidual epi{p->ffn2_b, sv.x1, y, nullptr, D, make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_OUT), d->seed_dev)};
-        GRB_CUDA((launch_gemm<0, 0>(sv.hact, (const bf16*)p->ffn2_w, T, D, 4 * D, 4 * D, 4 * D, 1, epi, st)));
+        GRB_CUDA(gemm_bias_res(sv.hact, (const bf16*)p->ffn2_w, p->ffn2_b, sv.x1, nullptr, y, T, D, 4 * D,
+                               make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_OUT), d->seed_dev), st));
     }
     return 0;
 }
@@ -316,22 +384,18 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     GRB_TRY(cast_bf16(dy, w.dyb, (size_t)T * D, D, drop_out, nullptr, st));
     GRB_TRY(colsum(w.dyb, T, D, D, g->ffn2_b, st));
     {
-        EpiAtomicF32 epi{g->ffn2_w, 4 * D, 1.f};  // dW2[D,4D] += dyb^T h
-        GRB_CUDA((launch_gemm<1, 1>(w.dyb, sv.hact, D, 4 * D, T, D, 4 * D, splitk_for(D, 4 * D, T), epi, st)));
+        GRB_CUDA(gemm_tn_atomic(w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, st));  // dW2[D,4D] += dyb^T h
     }
     {
-        EpiDAct<0> epi{sv.z1, w.dz1, 4 * D, drop_hid};  // dz1 = dropmask(dyb W2) * silu'(z1)
-        GRB_CUDA((launch_gemm<0, 1>(w.dyb, (const bf16*)p->ffn2_w, T, 4 * D, D, D, 4 * D, 1, epi, st)));
+        GRB_CUDA(gemm_dact(1, w.dyb, (const bf16*)p->ffn2_w, sv.z1, w.dz1, T, 4 * D, D, drop_hid, st));  // dz1 = dropmask(dyb W2) * silu'(z1)
     }
     // FFN first linear
     GRB_TRY(colsum(w.dz1, T, 4 * D, 4 * D, g->ffn1_b, st));
     {
-        EpiAtomicF32 epi{g->ffn1_w, D, 1.f};  // dW1[4D,D] += dz1^T xn
-        GRB_CUDA((launch_gemm<1, 1>(w.dz1, sv.xn, 4 * D, D, T, 4 * D, D, splitk_for(4 * D, D, T), epi, st)));
+        GRB_CUDA(gemm_tn_atomic(w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, st));  // dW1[4D,D] += dz1^T xn
     }
     {
-        EpiF32 epi{w.dxn, nullptr, D, 1.f};  // dxn = dz1 W1
-        GRB_CUDA((launch_gemm<0, 1>(w.dz1, (const bf16*)p->ffn1_w, T, D, 4 * D, 4 * D, D, 1, epi, st)));
+        GRB_CUDA(gemm_nn_f32(w.dz1, (const bf16*)p->ffn1_w, w.dxn, nullptr, 1.f, T, D, 4 * D, 4 * D, D, st));  // dxn = dz1 W1
     }
     // LN2 + residual + gate + LN1
     {
@@ -354,12 +418,10 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     // projection
     GRB_TRY(colsum(w.dzp, T, 4 * D, 4 * D, g->proj_b, st));
     {
-        EpiAtomicF32 epi{g->proj_w, D, 1.f};  // dWp[4D,D] += dzp^T xb
-        GRB_CUDA((launch_gemm<1, 1>(w.dzp, sv.xb, 4 * D, D, T, 4 * D, D, splitk_for(4 * D, D, T), epi, st)));
+        GRB_CUDA(gemm_tn_atomic(w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, st));  // dWp[4D,D] += dzp^T xb
     }
     {
-        EpiF32 epi{dx, w.dx1, D, 1.f};  // dx = dx1 + dzp Wp
-        GRB_CUDA((launch_gemm<0, 1>(w.dzp, (const bf16*)p->proj_w, T, D, 4 * D, 4 * D, D, 1, epi, st)));
+        GRB_CUDA(gemm_nn_f32(w.dzp, (const bf16*)p->proj_w, dx, w.dx1, 1.f, T, D, 4 * D, 4 * D, D, st));  // dx = dx1 + dzp Wp
     }
     (void)nodrop;
     return 0;
@@ -425,8 +487,7 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
     }
     {
-        EpiBf16 epi{h.logits, h.ldl};  // logits = xf E^T                                      (hstu.py:137)
-        GRB_CUDA((launch_gemm<0, 0>(h.xf, (const bf16*)table_bf16, T, C, D, D, D, 1, epi, st)));
+        GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     }
     ce_count_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(targets), T, h.scal, loss);
     GRB_CUDA(cudaGetLastError());
@@ -434,12 +495,10 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     GRB_CUDA(cudaGetLastError());
     if (!want_grad) return 0;
     {
-        EpiF32 epi{h.dxf, nullptr, D, 1.f};  // dxf = dlogits E
-        GRB_CUDA((launch_gemm<0, 1>(h.logits, (const bf16*)table_bf16, T, D, C, h.ldl, D, 1, epi, st)));
+        GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
     }
     {
-        EpiAtomicF32 epi{dtable, D, 1.f};  // dE[C,D] += dlogits^T xf
-        GRB_CUDA((launch_gemm<1, 1>(h.logits, h.xf, C, D, T, h.ldl, D, splitk_for(C, D, T), epi, st)));
+        GRB_CUDA(gemm_tn_atomic(h.logits, h.xf, dtable, C, D, T, h.ldl, D, st));  // dE[C,D] += dlogits^T xf
     }
     {
         LnBwdArgs a{h.dxf, x, h.stf, ln_g, nullptr, dx, dln_g, dln_b, T, D};
@@ -458,8 +517,7 @@ int grb_head_logits(const float* x, const float* ln_g, const float* ln_b, float 
         LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
         GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
     }
-    EpiF32Scalar epi{logits, C, C};
-    GRB_CUDA((launch_gemm<0, 0>(h.xf, (const bf16*)table_bf16, T, C, D, D, D, 1, epi, st)));
+    GRB_CUDA(gemm_nt_f32_plain(h.xf, (const bf16*)table_bf16, logits, T, C, D, st));
     return 0;
 }
 
@@ -529,20 +587,9 @@ int grb_linear_forward(const void* x_bf16, const void* w_bf16, const float* bias
     GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dropout drop = make_dropout(dropout_p, seed, site, seed_dev);
-    if (act == 0) {
-        EpiBiasBf16 epi{bias, (bf16*)z_bf16, N};
-        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
-    } else if (act == 1) {
-        GRB_REQUIRE(act_bf16, "act output is null");
-        EpiBiasSilu epi{bias, (bf16*)z_bf16, (bf16*)act_bf16, N, drop};
-        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
-    } else if (act == 2) {
-        GRB_REQUIRE(act_bf16, "act output is null");
-        EpiBiasRelu epi{bias, (bf16*)z_bf16, (bf16*)act_bf16, N, drop};
-        GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, st)));
-    } else {
-        return fail(GRB_EINVAL, "unknown activation %d", act);
-    }
+    GRB_REQUIRE(act >= 0 && act <= 2, "unknown activation %d", act);
+    GRB_REQUIRE(act == 0 || act_bf16, "act output is null");
+    GRB_CUDA(gemm_bias_act(act, (const bf16*)x_bf16, (const bf16*)w_bf16, bias, (bf16*)z_bf16, (bf16*)act_bf16, T, N, K, drop, st));
     return 0;
 }
 int grb_linear_residual_forward(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual, const float* row_scale,
@@ -550,8 +597,8 @@ int grb_linear_residual_forward(const void* x_bf16, const void* w_bf16, const fl
                                 void* stream) {
     GRB_REQUIRE(x_bf16 && w_bf16 && bias && residual && y, "null argument");
     GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
-    EpiBiasResidual epi{bias, residual, y, row_scale, N, make_dropout(dropout_p, seed, site, seed_dev)};
-    GRB_CUDA((launch_gemm<0, 0>((const bf16*)x_bf16, (const bf16*)w_bf16, T, N, K, K, K, 1, epi, static_cast<cudaStream_t>(stream))));
+    GRB_CUDA(gemm_bias_res((const bf16*)x_bf16, (const bf16*)w_bf16, bias, residual, row_scale, y, T, N, K,
+                           make_dropout(dropout_p, seed, site, seed_dev), static_cast<cudaStream_t>(stream)));
     return 0;
 }
 int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_bf16, int T, int N, int K, float* dx_f32,
@@ -562,12 +609,10 @@ int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_b
     if (db) GRB_TRY(colsum((const bf16*)dy_bf16, T, N, N, db, st));
     if (dw) {
         GRB_REQUIRE(x_bf16, "x is null");
-        EpiAtomicF32 epi{dw, K, 1.f};
-        GRB_CUDA((launch_gemm<1, 1>((const bf16*)dy_bf16, (const bf16*)x_bf16, N, K, T, N, K, splitk_for(N, K, T), epi, st)));
+        GRB_CUDA(gemm_tn_atomic((const bf16*)dy_bf16, (const bf16*)x_bf16, dw, N, K, T, N, K, st));
     }
     if (dx_f32) {
-        EpiF32 epi{dx_f32, dx_residual, K, 1.f};
-        GRB_CUDA((launch_gemm<0, 1>((const bf16*)dy_bf16, (const bf16*)w_bf16, T, K, N, N, K, 1, epi, st)));
+        GRB_CUDA(gemm_nn_f32((const bf16*)dy_bf16, (const bf16*)w_bf16, dx_f32, dx_residual, 1.f, T, K, N, N, K, st));
     }
     return 0;
 }

@@ -317,10 +317,14 @@ def rq_residual_argmin(x: torch.Tensor, codebooks: torch.Tensor, commitment: flo
     cb = codebooks.detach().contiguous().float()
     N, D = x.shape
     levels, K, _ = cb.shape
+    if D not in (32, 64):
+        raise _lib.GrbError(f"genrec_b200 error -1: latent dim {D} unsupported (32, 64)")
     ids = torch.empty(N, levels, dtype=torch.int64, device=x.device)
     emb = torch.empty(N, D, levels, dtype=torch.float32, device=x.device) if want_aux else None
     res = torch.empty(N, D, levels, dtype=torch.float32, device=x.device) if want_aux else None
     loss = torch.empty(N, dtype=torch.float32, device=x.device) if want_aux else None
+    if N == 0:
+        return ids, emb, res, loss
     check(lib.grb_rq_residual_argmin(ptr(x), ptr(cb), N, D, K, levels, float(commitment), ptr(ids), ptr(emb), ptr(res), ptr(loss), None,
                                      stream_ptr(x.device)))
     _lib.count_launches(1)

@@ -166,11 +166,11 @@ def test_dropout_statistics_and_reseed():
     assert torch.allclose(kept, torch.full_like(kept, 1.25), atol=1e-5)
     _, l1 = m(ids, ts, tg)
     _, l2 = m(ids, ts, tg)
-    assert l1.item() != l2.item()          # device seed counter advanced -> different masks
+    assert abs(l1.item() - l2.item()) > 1e-4   # device seed counter advanced -> different masks
     m.eval()
     _, e1 = m(ids, ts, tg)
     _, e2 = m(ids, ts, tg)
-    assert e1.item() == e2.item()
+    assert abs(e1.item() - e2.item()) < 1e-5   # (float atomics in the loss reduction: not bit-deterministic)
     # gradient flows with dropout on and is finite
     m.train()
     _, l = m(ids, ts, tg)
