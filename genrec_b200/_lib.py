@@ -34,7 +34,7 @@ class HstuLayerGrads(C.Structure):
 
 
 class HstuSeq(C.Structure):
-    _fields_ = [("pad", c_void_p), ("timestamps", c_void_p), ("pos_bucket", c_void_p), ("time_thr", c_void_p)]
+    _fields_ = [("mask_bucket", c_void_p), ("ld_mask", c_int), ("has_time", c_int), ("pos_bucket", c_void_p)]
 
 
 class SasrecDims(C.Structure):
@@ -53,6 +53,7 @@ SIGNATURES = {
     "grb_hstu_layer_forward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p, c_void_p]),
     "grb_hstu_layer_backward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p,
                                         P(HstuLayerGrads), c_void_p, c_void_p]),
+    "grb_hstu_mask_bucket": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "grb_embed_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                   c_float, c_u64, c_void_p, c_void_p]),
     "grb_embed_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float,

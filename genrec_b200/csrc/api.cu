@@ -15,6 +15,8 @@
 #include "rowwise.cuh"
 #include "rq_argmin.cuh"
 #include "tc_gemm.cuh"
+#include "tc_ce.cuh"
+#include "tc_tn_group.cuh"
 #include <cstdlib>
 
 using namespace grb;
@@ -94,9 +96,9 @@ int tn_splits(int M, int N, int K) {
 cudaError_t gemm_bias_act(int act, const bf16* x, const bf16* w, const float* bias, bf16* z, bf16* a, int M, int N, int K, const Dropout& drop,
                           cudaStream_t st) {
     if (use_tc()) {
-        if (act == 0) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<0>{bias, z, a, N, drop}, sm_count(), st);
-        if (act == 1) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<1>{bias, z, a, N, drop}, sm_count(), st);
-        return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<2>{bias, z, a, N, drop}, sm_count(), st);
+        if (act == 0) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<0>{bias, N, drop}, z, nullptr, N, sm_count(), st);
+        if (act == 1) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<1>{bias, N, drop}, z, a, N, sm_count(), st);
+        return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasAct<2>{bias, N, drop}, z, a, N, sm_count(), st);
     }
     if (act == 0) return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasBf16{bias, z, N}, st);
     if (act == 1) return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasSilu{bias, z, a, N, drop}, st);
@@ -105,14 +107,14 @@ cudaError_t gemm_bias_act(int act, const bf16* x, const bf16* w, const float* bi
 // y = res + drop(x W^T + b) (* row_scale)   (NT)
 cudaError_t gemm_bias_res(const bf16* x, const bf16* w, const float* bias, const float* res, const float* row_scale, float* y, int M, int N,
                           int K, const Dropout& drop, cudaStream_t st) {
-    if (use_tc()) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasResidual{bias, res, y, row_scale, N, drop}, sm_count(), st);
+    if (use_tc()) return launch_tc_gemm<0, 0>(x, w, M, N, K, K, K, 1, TcEpiBiasResidual{bias, res, row_scale, N, drop}, y, nullptr, N, sm_count(), st);
     return launch_gemm<0, 0>(x, w, M, N, K, K, K, 1, EpiBiasResidual{bias, res, y, row_scale, N, drop}, st);
 }
 // g[M,N] = dropmask(dy[M,K] W[K,N]) * act'(z)   (NN) ; act 1 silu, 2 relu
 cudaError_t gemm_dact(int act, const bf16* dy, const bf16* w, const bf16* z, bf16* g, int M, int N, int K, const Dropout& drop, cudaStream_t st) {
     if (use_tc()) {
-        if (act == 1) return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<1>{z, g, N, drop}, sm_count(), st);
-        return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<2>{z, g, N, drop}, sm_count(), st);
+        if (act == 1) return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<1>{z, N, drop}, g, nullptr, N, sm_count(), st);
+        return launch_tc_gemm<0, 1>(dy, w, M, N, K, K, N, 1, TcEpiDAct<2>{z, N, drop}, g, nullptr, N, sm_count(), st);
     }
     if (act == 1) return launch_gemm<0, 1>(dy, w, M, N, K, K, N, 1, EpiDAct<0>{z, g, N, drop}, st);
     return launch_gemm<0, 1>(dy, w, M, N, K, K, N, 1, EpiDAct<1>{z, g, N, drop}, st);
@@ -120,22 +122,22 @@ cudaError_t gemm_dact(int act, const bf16* dy, const bf16* w, const bf16* z, bf1
 // out[M,N] fp32 = scale * A[M,K] B[K,N] (+ res)   (NN)
 cudaError_t gemm_nn_f32(const bf16* A, const bf16* B, float* out, const float* res, float scale, int M, int N, int K, int lda, int ldb,
                         cudaStream_t st) {
-    if (use_tc()) return launch_tc_gemm<0, 1>(A, B, M, N, K, lda, ldb, 1, TcEpiF32{out, res, N, scale}, sm_count(), st);
+    if (use_tc()) return launch_tc_gemm<0, 1>(A, B, M, N, K, lda, ldb, 1, TcEpiF32{res, N, scale}, out, nullptr, N, sm_count(), st);
     return launch_gemm<0, 1>(A, B, M, N, K, lda, ldb, 1, EpiF32{out, res, N, scale}, st);
 }
 // out[M,N] fp32 += A^T B with A stored [K,M], B stored [K,N]   (TN, split-K, atomics)
 cudaError_t gemm_tn_atomic(const bf16* A, const bf16* B, float* out, int M, int N, int K, int lda, int ldb, cudaStream_t st) {
-    if (use_tc()) return launch_tc_gemm<1, 1>(A, B, M, N, K, lda, ldb, tn_splits(M, N, K), TcEpiAtomicF32{out, N, 1.f}, sm_count(), st);
+    if (use_tc()) return launch_tc_gemm<1, 1>(A, B, M, N, K, lda, ldb, tn_splits(M, N, K), TcEpiAtomicF32{out, N, 1.f}, nullptr, nullptr, 0, sm_count(), st);
     return launch_gemm<1, 1>(A, B, M, N, K, lda, ldb, splitk_for(M, N, K), EpiAtomicF32{out, N, 1.f}, st);
 }
 // out[M,N] bf16 (leading dim ldo) = A[M,K] B[N,K]^T   (NT)
 cudaError_t gemm_nt_bf16(const bf16* A, const bf16* B, bf16* out, int ldo, int M, int N, int K, cudaStream_t st) {
-    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiBf16{out, ldo}, sm_count(), st);
+    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiBf16{}, out, nullptr, ldo, sm_count(), st);
     return launch_gemm<0, 0>(A, B, M, N, K, K, K, 1, EpiBf16{out, ldo}, st);
 }
 // out[M,N] fp32 (leading dim N, any parity) = A B^T   (NT)
 cudaError_t gemm_nt_f32_plain(const bf16* A, const bf16* B, float* out, int M, int N, int K, cudaStream_t st) {
-    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiF32Plain{out, N}, sm_count(), st);
+    if (use_tc()) return launch_tc_gemm<0, 0>(A, B, M, N, K, K, K, 1, TcEpiF32Plain{out, N}, nullptr, nullptr, 0, sm_count(), st);
     return launch_gemm<0, 0>(A, B, M, N, K, K, K, 1, EpiF32Scalar{out, N, N}, st);
 }
 
@@ -219,14 +221,13 @@ HstuAttnArgs make_attn_args(const grb_hstu_dims* d, const grb_hstu_layer_params*
     const int D = d->D;
     a.q = sv.P + 2 * D; a.k = sv.P + 3 * D; a.v = sv.P + D;
     a.ldq = a.ldk = a.ldv = 4 * D;
-    a.pad = s->pad;
     a.B = d->B; a.L = d->L; a.H = d->H;
     a.bias.wpos = p->pos_table;
     a.bias.pos_bucket = s->pos_bucket;
-    const bool has_time = p->time_table != nullptr && s->timestamps != nullptr && d->ntime > 0;
+    const bool has_time = p->time_table != nullptr && s->has_time && d->ntime > 0;
     a.bias.wtime = has_time ? p->time_table : nullptr;
-    a.bias.time_thr = reinterpret_cast<const long long*>(s->time_thr);
-    a.bias.ts = has_time ? reinterpret_cast<const long long*>(s->timestamps) : nullptr;
+    a.bias.mask_bucket = s->mask_bucket;
+    a.bias.ldmb = s->ld_mask;
     a.bias.npos = d->npos;
     a.bias.ntime = has_time ? d->ntime : 0;
     a.o = sv.O; a.ldo = D;
@@ -238,7 +239,7 @@ int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
     size_t smem = sizeof(AttSmem<DH>) + align_up(a.L, 16);
     GRB_TRY(set_smem(hstu_attn_fwd_kernel<DH>, smem));
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
-    hstu_attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(a, a.bias.pos_bucket);
+    hstu_attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -248,11 +249,11 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     size_t posb = align_up(a.L, 16);
     size_t smem_q = sizeof(AttSmem<DH>) + posb;
     GRB_TRY(set_smem(hstu_attn_bwd_dq_kernel<DH>, smem_q));
-    hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a, a.bias.pos_bucket);
+    hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
     GRB_CUDA(cudaGetLastError());
     size_t smem_k = sizeof(AttSmem<DH>) + posb + (size_t)4 * (a.bias.ntime + a.bias.npos) * 32 * sizeof(float);
     GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
-    hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, a.bias.pos_bucket, (int)posb);
+    hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, (int)posb);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -325,7 +326,8 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
     GRB_REQUIRE(p && s && x && y && saved, "null argument");
     GRB_REQUIRE(p->proj_w && p->proj_b && p->pos_table && p->ln1_g && p->ln1_b && p->ffn1_w && p->ffn1_b && p->ffn2_w &&
                     p->ffn2_b && p->ln2_g && p->ln2_b, "null parameter pointer");
-    GRB_REQUIRE(s->pad && s->pos_bucket && s->time_thr, "null sequence metadata");
+    GRB_REQUIRE(s->mask_bucket && s->pos_bucket, "null sequence metadata");
+    GRB_REQUIRE(s->ld_mask >= d->L && s->ld_mask % 16 == 0 && aligned16(s->mask_bucket), "mask_bucket pitch must be a multiple of 16 and >= L");
     GRB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(saved) && aligned16(p->proj_w) && aligned16(p->ffn1_w) && aligned16(p->ffn2_w),
                 "buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -384,7 +386,7 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     GRB_TRY(cast_bf16(dy, w.dyb, (size_t)T * D, D, drop_out, nullptr, st));
     GRB_TRY(colsum(w.dyb, T, D, D, g->ffn2_b, st));
     {
-        GRB_CUDA(gemm_tn_atomic(w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, st));  // dW2[D,4D] += dyb^T h
+        if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, st));  // dW2[D,4D] += dyb^T h
     }
     {
         GRB_CUDA(gemm_dact(1, w.dyb, (const bf16*)p->ffn2_w, sv.z1, w.dz1, T, 4 * D, D, drop_hid, st));  // dz1 = dropmask(dyb W2) * silu'(z1)
@@ -392,7 +394,7 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     // FFN first linear
     GRB_TRY(colsum(w.dz1, T, 4 * D, 4 * D, g->ffn1_b, st));
     {
-        GRB_CUDA(gemm_tn_atomic(w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, st));  // dW1[4D,D] += dz1^T xn
+        if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, st));  // dW1[4D,D] += dz1^T xn
     }
     {
         GRB_CUDA(gemm_nn_f32(w.dz1, (const bf16*)p->ffn1_w, w.dxn, nullptr, 1.f, T, D, 4 * D, 4 * D, D, st));  // dxn = dz1 W1
@@ -418,12 +420,32 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     // projection
     GRB_TRY(colsum(w.dzp, T, 4 * D, 4 * D, g->proj_b, st));
     {
-        GRB_CUDA(gemm_tn_atomic(w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, st));  // dWp[4D,D] += dzp^T xb
+        if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, st));  // dWp[4D,D] += dzp^T xb
     }
     {
         GRB_CUDA(gemm_nn_f32(w.dzp, (const bf16*)p->proj_w, dx, w.dx1, 1.f, T, D, 4 * D, 4 * D, D, st));  // dx = dx1 + dzp Wp
     }
+    if (use_tc()) {
+        // the three weight gradients of the layer in ONE grouped launch: dW2 += dyb^T h, dW1 += dz1^T xn, dWp += dzp^T xb
+        TnSpec specs[3] = {{w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, 4 * D},
+                           {w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, D},
+                           {w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, D}};
+        GRB_CUDA(launch_tc_tn_group(specs, 3, sm_count(), st));
+    }
     (void)nodrop;
+    return 0;
+}
+
+int grb_hstu_mask_bucket(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, int B, int L, int ntime, uint8_t* out,
+                         int ld_mask, void* stream) {
+    GRB_REQUIRE(pad && time_thr && out, "null argument");
+    GRB_REQUIRE(B > 0 && L > 0 && B <= 65535 && L <= 65535, "bad shape B=%d L=%d", B, L);
+    GRB_REQUIRE(ld_mask >= L && ld_mask % 16 == 0, "ld_mask must be a multiple of 16 and >= L");
+    GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS, "num_time_buckets out of range");
+    dim3 grid((ld_mask + 255) / 256, L, B);
+    hstu_mask_bucket_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(timestamps), pad,
+                                                                                  reinterpret_cast<const long long*>(time_thr), L, ld_mask, ntime, out);
+    GRB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -486,13 +508,22 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
         GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
     }
-    {
-        GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
-    }
     ce_count_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(targets), T, h.scal, loss);
     GRB_CUDA(cudaGetLastError());
-    ce_fwd_bwd_kernel<<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
+    if (use_tc()) {
+        // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly              (hstu.py:137-146)
+        const long long* tg = reinterpret_cast<const long long*>(targets);
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
+    } else {
+    GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
+    if (h.ldl / 8 <= 256 * 8)
+        ce_fwd_bwd_vec_kernel<8><<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
+    else
+        ce_fwd_bwd_kernel<<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
     GRB_CUDA(cudaGetLastError());
+    }
     if (!want_grad) return 0;
     {
         GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E

@@ -1,12 +1,18 @@
-// genrec_b200 - HSTU pointwise (SiLU) attention, forward and backward, first-generation mma.sync path.
+// genrec_b200 - HSTU pointwise (SiLU) attention, forward and backward (mma.sync m16n8k16 path).
 //
 //   S[b,h,i,j] = Q_i . K_j + Wpos[pb(i-j), h] + Wtime[tb(|ts_i - ts_j|), h]
 //   valid      = (j <= i) and not pad[b,j]
 //   A          = valid ? silu(S) : 0          O = A V
-// (reference: genrec/models/hstu.py:244-267).  No [L,L] tensor ever reaches HBM.
+// (reference: genrec/models/hstu.py:244-267).  No [L,L] fp tensor ever reaches HBM.
+//
+// All integer work is hoisted out of the per-head / per-layer kernels: `hstu_mask_bucket_kernel` runs ONCE per batch and
+// writes one byte per (b, i, j): the temporal bucket of |ts_i - ts_j| (integer-threshold form of the reference's
+// fp32 log / 0.693 expression), or 255 when the cell is masked (j > i, padded key).  The 5 MB byte matrix (cfg-2) stays
+// L2-resident and is re-used by every head of every layer, forward and backward (4 layers x 3 kernels x 4 heads).
 //
 // Layout: Q/K/V/dO/O are row-major [T = B*L, ld] bf16 with head h at columns h*DH .. h*DH+DH-1.
 // One CTA = 4 warps = 64 query rows (fwd, dQ) or 64 key rows (dK/dV); KV (resp. Q) tiles of 64 stream through smem.
+// Warps whose rows lie beyond L, and 8-key column blocks above the causal diagonal, are skipped (warp-uniform branches).
 #pragma once
 #include "common.cuh"
 
@@ -15,20 +21,21 @@ namespace grb {
 constexpr int ATT_BLK = 64;       // rows per CTA and per streamed tile
 constexpr int ATT_THREADS = 128;  // 4 warps x 16 rows
 constexpr int ATT_MAX_BUCKETS = 64;
+constexpr int ATT_MB_LD = ATT_BLK + 16;  // padded row (bytes) of the mask/bucket tile in smem
+constexpr unsigned ATT_MASKED = 255u;
 
 struct HstuBiasArgs {
     const float* wpos;           // [npos, H]
     const uint8_t* pos_bucket;   // [L]   bucket of delta = i - j >= 0  (host: reference bucketing of clamp(j - i, 0) -> all 0)
     const float* wtime;          // [ntime, H] or null
-    const long long* time_thr;   // [65] thr[k] = min |dt| whose reference bucket >= k ; thr[64] = INT64_MAX
-    const long long* ts;         // [B, L] or null
+    const uint8_t* mask_bucket;  // [B, L, ldmb]  temporal bucket (0 if no temporal bias) or 255 = masked
+    int ldmb;
     int npos, ntime;
 };
 
 struct HstuAttnArgs {
     const bf16* q; const bf16* k; const bf16* v;   // forward operands (activations after SiLU)
     int ldq, ldk, ldv;
-    const uint8_t* pad;  // [B, L] 1 = padded key
     int B, L, H;
     HstuBiasArgs bias;
     // forward
@@ -41,23 +48,36 @@ struct HstuAttnArgs {
     float* dwtime;  // [ntime, H] accumulated
 };
 
-GRB_DEVINL int time_bucket_dev(long long dt, const long long* s_thr, int ntime) {
+GRB_DEVINL int time_bucket_dev(long long dt, const long long* thr, int ntime) {
     long long d = dt < 0 ? -dt : dt;
     d = d < 1 ? 1 : d;
     int e = 63 - __clzll(d);
-    int b = e + (d >= s_thr[e + 1] ? 1 : 0);
+    int b = e + (d >= thr[e + 1] ? 1 : 0);
     return min(b, ntime - 1);
+}
+
+// out[b, i, j] = (j <= i && !pad[b, j]) ? bucket(|ts[b,i] - ts[b,j]|) : 255        grid (ceil(ld/256), L, B)
+__global__ void __launch_bounds__(256) hstu_mask_bucket_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad,
+                                                              const long long* __restrict__ thr_g, int L, int ld, int ntime,
+                                                              uint8_t* __restrict__ out) {
+    __shared__ long long thr[ATT_MAX_BUCKETS + 1];
+    for (int i = threadIdx.x; i <= ATT_MAX_BUCKETS; i += 256) thr[i] = thr_g[i];
+    __syncthreads();
+    const int b = blockIdx.z, i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= ld) return;
+    const size_t row = (size_t)b * L;
+    unsigned v = ATT_MASKED;
+    if (j <= i && j < L && pad[row + j] == 0) v = (ts != nullptr && ntime > 0) ? (unsigned)time_bucket_dev(ts[row + i] - ts[row + j], thr, ntime) : 0u;
+    out[(row + i) * ld + j] = (uint8_t)v;
 }
 
 template <int DH>
 struct AttSmem {
     static constexpr int LD = DH + 8;
     bf16 tile[4][ATT_BLK * LD];  // roles differ per kernel
-    long long ts_tile[ATT_BLK];
-    long long thr[ATT_MAX_BUCKETS + 1];
     float wpos[ATT_MAX_BUCKETS];
     float wtime[ATT_MAX_BUCKETS];
-    uint8_t pad_tile[ATT_BLK];
+    uint8_t mb[ATT_BLK * ATT_MB_LD];  // [query row][key col] bytes of the current (q tile, kv tile) pair
 };
 
 // cooperative 64 x DH tile load (rows row0.. of one batch element, zero-filled beyond L)
@@ -72,6 +92,15 @@ GRB_DEVINL void att_load_tile(bf16* s, const bf16* g, int ld, long long tok0, in
         cp_async16(s + r * LD + kc, src, ok ? 16 : 0);
     }
 }
+// 64 x 64 byte tile of the mask/bucket matrix: rows q0.., cols k0.. (ldmb is a multiple of 16 and >= the padded width)
+GRB_DEVINL void att_load_mb(uint8_t* s, const uint8_t* g, int ldmb, long long tok0, int q0, int k0, int L, int tid) {
+    for (int c = tid; c < ATT_BLK * 4; c += ATT_THREADS) {
+        int r = c >> 2, kc = (c & 3) * 16;
+        bool ok = (q0 + r) < L && (k0 + kc) < ldmb;
+        if (ok) cp_async16(s + r * ATT_MB_LD + kc, g + (size_t)(tok0 + q0 + r) * ldmb + k0 + kc, 16);
+        else *reinterpret_cast<uint4*>(s + r * ATT_MB_LD + kc) = make_uint4(~0u, ~0u, ~0u, ~0u);  // out of range == masked
+    }
+}
 
 template <int DH>
 GRB_DEVINL void att_load_bias_tables(AttSmem<DH>& sm, const HstuBiasArgs& b, int h, int H, int tid) {
@@ -79,7 +108,6 @@ GRB_DEVINL void att_load_bias_tables(AttSmem<DH>& sm, const HstuBiasArgs& b, int
         sm.wpos[i] = i < b.npos ? b.wpos[i * H + h] : 0.f;
         sm.wtime[i] = (b.wtime && i < b.ntime) ? b.wtime[i * H + h] : 0.f;
     }
-    for (int i = tid; i <= ATT_MAX_BUCKETS; i += ATT_THREADS) sm.thr[i] = b.time_thr ? b.time_thr[i] : 0x7fffffffffffffffLL;
 }
 
 // A-operand fragments of a 16 x DH slab (rows wrow..wrow+15 of an smem tile)
@@ -90,34 +118,40 @@ GRB_DEVINL void att_load_afrag(uint32_t (&f)[DH / 16][4], const bf16* tile, int 
     for (int ks = 0; ks < DH / 16; ++ks) ldsm_x4(f[ks], tile + (wrow + lane_a_row(lane)) * LD + ks * 16 + lane_a_col(lane));
 }
 
-// acc[8][4] (16 rows x 64 cols) = Afrag(16 x DH) * Tile^T   where Tile is [64][DH] (k = DH contiguous)
+// acc[8][4] (16 rows x 64 cols) = Afrag(16 x DH) * Tile^T   where Tile is [64][DH] (k = DH contiguous); only the first
+// `npairs` pairs of 8-column blocks are computed (warp-uniform)
 template <int DH>
-GRB_DEVINL void att_mma_nt(float (&acc)[8][4], const uint32_t (&af)[DH / 16][4], const bf16* tile, int lane) {
+GRB_DEVINL void att_mma_nt(float (&acc)[8][4], const uint32_t (&af)[DH / 16][4], const bf16* tile, int lane, int npairs = 4) {
     constexpr int LD = DH + 8;
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-            uint32_t r[4];
-            ldsm_x4(r, tile + (j2 * 16 + lane_b_row(lane)) * LD + ks * 16 + lane_b_col(lane));
-            mma_bf16(acc[2 * j2], af[ks], r[0], r[1]);
-            mma_bf16(acc[2 * j2 + 1], af[ks], r[2], r[3]);
+            if (j2 < npairs) {
+                uint32_t r[4];
+                ldsm_x4(r, tile + (j2 * 16 + lane_b_row(lane)) * LD + ks * 16 + lane_b_col(lane));
+                mma_bf16(acc[2 * j2], af[ks], r[0], r[1]);
+                mma_bf16(acc[2 * j2 + 1], af[ks], r[2], r[3]);
+            }
         }
     }
 }
 
 // out[DH/8][4] (16 rows x DH cols) += P(16 x 64, as 4 k16 A-fragments) * Tile   where Tile is [64][DH] (n = DH contiguous)
+// only k16 blocks [kbeg, kend) contribute (warp-uniform)
 template <int DH>
-GRB_DEVINL void att_mma_nn(float (&out)[DH / 8][4], const uint32_t (&pf)[4][4], const bf16* tile, int lane) {
+GRB_DEVINL void att_mma_nn(float (&out)[DH / 8][4], const uint32_t (&pf)[4][4], const bf16* tile, int lane, int kbeg = 0, int kend = 4) {
     constexpr int LD = DH + 8;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= kbeg && kk < kend) {
 #pragma unroll
-        for (int n2 = 0; n2 < DH / 16; ++n2) {
-            uint32_t r[4];
-            ldsm_x4_t(r, tile + (kk * 16 + lane_a_row(lane)) * LD + n2 * 16 + lane_a_col(lane));
-            mma_bf16(out[2 * n2], pf[kk], r[0], r[1]);
-            mma_bf16(out[2 * n2 + 1], pf[kk], r[2], r[3]);
+            for (int n2 = 0; n2 < DH / 16; ++n2) {
+                uint32_t r[4];
+                ldsm_x4_t(r, tile + (kk * 16 + lane_a_row(lane)) * LD + n2 * 16 + lane_a_col(lane));
+                mma_bf16(out[2 * n2], pf[kk], r[0], r[1]);
+                mma_bf16(out[2 * n2 + 1], pf[kk], r[2], r[3]);
+            }
         }
     }
 }
@@ -135,19 +169,17 @@ GRB_DEVINL void att_pack_p(uint32_t (&pf)[4][4], const float (&s)[8][4]) {
 // ============================================================================================ forward
 // tile roles: 0 = Q, 1 = K, 2 = V
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs a, const uint8_t* __restrict__ posb_g) {
+__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs a) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
     uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);  // [L]
-    constexpr int LD = DH + 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
-    const bool has_time = a.bias.wtime != nullptr && a.bias.ts != nullptr;
 
     att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = posb_g[i];
+    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
     att_load_tile<DH>(sm.tile[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
     cp_async_commit();
     cp_async_wait<0>();
@@ -156,11 +188,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
     uint32_t qf[DH / 16][4];
     att_load_afrag<DH>(qf, sm.tile[0], warp * 16, lane);
     const int i0 = q0 + warp * 16 + g, i1 = i0 + 8;
-    long long ts_i0 = 0, ts_i1 = 0;
-    if (has_time) {
-        if (i0 < L) ts_i0 = a.bias.ts[tok0 + i0];
-        if (i1 < L) ts_i1 = a.bias.ts[tok0 + i1];
-    }
+    const bool warp_live = q0 + warp * 16 < L;  // warp-uniform
 
     float o[DH / 8][4];
 #pragma unroll
@@ -173,42 +201,43 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
         __syncthreads();  // previous tile fully consumed
         att_load_tile<DH>(sm.tile[1], a.k, a.ldk, tok0, k0, L, h * DH, tid);
         att_load_tile<DH>(sm.tile[2], a.v, a.ldv, tok0, k0, L, h * DH, tid);
+        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
         cp_async_commit();
-        if (tid < ATT_BLK) {
-            int j = k0 + tid;
-            sm.pad_tile[tid] = (j < L) ? a.pad[tok0 + j] : 1;
-            sm.ts_tile[tid] = (has_time && j < L) ? a.bias.ts[tok0 + j] : 0;
-        }
         cp_async_wait<0>();
         __syncthreads();
+        if (!warp_live) continue;
+        // 8-key blocks that intersect the causal triangle of this warp's 16 rows (diagonal tile only)
+        const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
+        const int npairs = (nblk + 1) >> 1;
 
         float s[8][4];
 #pragma unroll
         for (int n = 0; n < 8; ++n)
 #pragma unroll
             for (int r = 0; r < 4; ++r) s[n][r] = 0.f;
-        att_mma_nt<DH>(s, qf, sm.tile[1], lane);
+        att_mma_nt<DH>(s, qf, sm.tile[1], lane, npairs);
 
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
+            if (n < 2 * npairs) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int jl = n * 8 + 2 * t + (r & 1);
-                const int j = k0 + jl;
-                const int i = (r < 2) ? i0 : i1;
-                const bool valid = (j <= i) && (i < L) && (sm.pad_tile[jl] == 0);
-                float val = 0.f;
-                if (valid) {
-                    float bias = sm.wpos[s_posb[i - j]];
-                    if (has_time) bias += sm.wtime[time_bucket_dev(((r < 2) ? ts_i0 : ts_i1) - sm.ts_tile[jl], sm.thr, a.bias.ntime)];
-                    val = siluf(s[n][r] + bias);
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int il = warp * 16 + g + 8 * hf, i = q0 + il;
+                    const int jl = n * 8 + 2 * t, j = k0 + jl;
+                    const unsigned mb2 = *reinterpret_cast<const uint16_t*>(sm.mb + il * ATT_MB_LD + jl);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned bk = (mb2 >> (8 * e)) & 0xffu;
+                        float val = 0.f;
+                        if (bk != ATT_MASKED) val = siluf(s[n][2 * hf + e] + sm.wpos[s_posb[i - j - e]] + sm.wtime[bk]);
+                        s[n][2 * hf + e] = val;
+                    }
                 }
-                s[n][r] = val;
             }
         }
         uint32_t pf[4][4];
         att_pack_p(pf, s);
-        att_mma_nn<DH>(o, pf, sm.tile[2], lane);
+        att_mma_nn<DH>(o, pf, sm.tile[2], lane, 0, npairs);
     }
 
 #pragma unroll
@@ -222,7 +251,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
 // ============================================================================================ backward: dQ
 // tile roles: 0 = Q, 1 = K, 2 = V, 3 = dO
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnArgs a, const uint8_t* __restrict__ posb_g) {
+__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnArgs a) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
     uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);
@@ -230,10 +259,9 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
-    const bool has_time = a.bias.wtime != nullptr && a.bias.ts != nullptr;
 
     att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = posb_g[i];
+    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
     att_load_tile<DH>(sm.tile[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
     att_load_tile<DH>(sm.tile[3], a.d_o, a.lddo, tok0, q0, L, h * DH, tid);
     cp_async_commit();
@@ -244,11 +272,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
     att_load_afrag<DH>(qf, sm.tile[0], warp * 16, lane);
     att_load_afrag<DH>(dof, sm.tile[3], warp * 16, lane);
     const int i0 = q0 + warp * 16 + g, i1 = i0 + 8;
-    long long ts_i0 = 0, ts_i1 = 0;
-    if (has_time) {
-        if (i0 < L) ts_i0 = a.bias.ts[tok0 + i0];
-        if (i1 < L) ts_i1 = a.bias.ts[tok0 + i1];
-    }
+    const bool warp_live = q0 + warp * 16 < L;
     float dq[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n)
@@ -260,42 +284,43 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
         __syncthreads();
         att_load_tile<DH>(sm.tile[1], a.k, a.ldk, tok0, k0, L, h * DH, tid);
         att_load_tile<DH>(sm.tile[2], a.v, a.ldv, tok0, k0, L, h * DH, tid);
+        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
         cp_async_commit();
-        if (tid < ATT_BLK) {
-            int j = k0 + tid;
-            sm.pad_tile[tid] = (j < L) ? a.pad[tok0 + j] : 1;
-            sm.ts_tile[tid] = (has_time && j < L) ? a.bias.ts[tok0 + j] : 0;
-        }
         cp_async_wait<0>();
         __syncthreads();
+        if (!warp_live) continue;
+        const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
+        const int npairs = (nblk + 1) >> 1;
 
         float s[8][4], da[8][4];
 #pragma unroll
         for (int n = 0; n < 8; ++n)
 #pragma unroll
             for (int r = 0; r < 4; ++r) s[n][r] = 0.f, da[n][r] = 0.f;
-        att_mma_nt<DH>(s, qf, sm.tile[1], lane);    // S  = Q K^T
-        att_mma_nt<DH>(da, dof, sm.tile[2], lane);  // dA = dO V^T
+        att_mma_nt<DH>(s, qf, sm.tile[1], lane, npairs);    // S  = Q K^T
+        att_mma_nt<DH>(da, dof, sm.tile[2], lane, npairs);  // dA = dO V^T
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
+            if (n < 2 * npairs) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int jl = n * 8 + 2 * t + (r & 1);
-                const int j = k0 + jl;
-                const int i = (r < 2) ? i0 : i1;
-                const bool valid = (j <= i) && (i < L) && (sm.pad_tile[jl] == 0);
-                float val = 0.f;
-                if (valid) {
-                    float bias = sm.wpos[s_posb[i - j]];
-                    if (has_time) bias += sm.wtime[time_bucket_dev(((r < 2) ? ts_i0 : ts_i1) - sm.ts_tile[jl], sm.thr, a.bias.ntime)];
-                    val = da[n][r] * dsiluf(s[n][r] + bias);
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int il = warp * 16 + g + 8 * hf, i = q0 + il;
+                    const int jl = n * 8 + 2 * t, j = k0 + jl;
+                    const unsigned mb2 = *reinterpret_cast<const uint16_t*>(sm.mb + il * ATT_MB_LD + jl);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned bk = (mb2 >> (8 * e)) & 0xffu;
+                        float val = 0.f;
+                        if (bk != ATT_MASKED)
+                            val = da[n][2 * hf + e] * dsiluf(s[n][2 * hf + e] + sm.wpos[s_posb[i - j - e]] + sm.wtime[bk]);
+                        s[n][2 * hf + e] = val;  // dS
+                    }
                 }
-                s[n][r] = val;  // dS
             }
         }
         uint32_t pf[4][4];
         att_pack_p(pf, s);
-        att_mma_nn<DH>(dq, pf, sm.tile[1], lane);  // dQ += dS K
+        att_mma_nn<DH>(dq, pf, sm.tile[1], lane, 0, npairs);  // dQ += dS K
     }
 
 #pragma unroll
@@ -320,8 +345,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
 // CTA owns 64 keys; tile roles: 0 = K (own), 1 = V (own), 2 = Q (streamed), 3 = dO (streamed)
 // dynamic smem tail: s_posb[L] (padded to 16) then lane-private histograms  hist_t[4][ntime][32], hist_p[4][npos][32]
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, const uint8_t* __restrict__ posb_g,
-                                                                         int posb_bytes) {
+__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int posb_bytes) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
     uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);
@@ -332,11 +356,11 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
     const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, k0 = kt * ATT_BLK;
     const long long tok0 = (long long)b * L;
-    const bool has_time = a.bias.wtime != nullptr && a.bias.ts != nullptr;
+    const bool has_time = a.bias.wtime != nullptr && ntime > 0;
     const int nqt = (L + ATT_BLK - 1) / ATT_BLK;
 
     att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = posb_g[i];
+    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
     for (int i = tid; i < 4 * (ntime + npos) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
     att_load_tile<DH>(sm.tile[0], a.k, a.ldk, tok0, k0, L, h * DH, tid);
     att_load_tile<DH>(sm.tile[1], a.v, a.ldv, tok0, k0, L, h * DH, tid);
@@ -348,10 +372,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
     att_load_afrag<DH>(kf, sm.tile[0], warp * 16, lane);
     att_load_afrag<DH>(vf, sm.tile[1], warp * 16, lane);
     const int j0 = k0 + warp * 16 + g, j1 = j0 + 8;
-    long long ts_j0 = 0, ts_j1 = 0;
-    bool ok_j0 = false, ok_j1 = false;  // key exists and is not padding
-    if (j0 < L) { ok_j0 = a.pad[tok0 + j0] == 0; if (has_time) ts_j0 = a.bias.ts[tok0 + j0]; }
-    if (j1 < L) { ok_j1 = a.pad[tok0 + j1] == 0; if (has_time) ts_j1 = a.bias.ts[tok0 + j1]; }
+    const bool warp_live = k0 + warp * 16 < L;
 
     float dk[DH / 8][4], dv[DH / 8][4];
 #pragma unroll
@@ -366,13 +387,14 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
         __syncthreads();
         att_load_tile<DH>(sm.tile[2], a.q, a.ldq, tok0, q0, L, h * DH, tid);
         att_load_tile<DH>(sm.tile[3], a.d_o, a.lddo, tok0, q0, L, h * DH, tid);
+        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
         cp_async_commit();
-        if (tid < ATT_BLK) {
-            int i = q0 + tid;
-            sm.ts_tile[tid] = (has_time && i < L) ? a.bias.ts[tok0 + i] : 0;
-        }
         cp_async_wait<0>();
         __syncthreads();
+        if (!warp_live) continue;
+        // query 8-blocks that can see this warp's keys (diagonal tile: queries >= first key of the warp)
+        const int nb0 = (qt == kt) ? 2 * warp : 0;          // first live 8-query block (warp-uniform)
+        const int kb0 = nb0 >> 1;                            // first live k16 block for the second GEMMs
 
         float st[8][4], dat[8][4];
 #pragma unroll
@@ -383,36 +405,35 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
         att_mma_nt<DH>(dat, vf, sm.tile[3], lane);  // dA^T = V dO^T
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
+            if (n >= nb0) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int il = n * 8 + 2 * t + (r & 1);
-                const int i = q0 + il;
-                const int j = (r < 2) ? j0 : j1;
-                const bool valid = (j <= i) && (i < L) && ((r < 2) ? ok_j0 : ok_j1);
-                float av = 0.f, dsv = 0.f;
-                if (valid) {
-                    int pbk = s_posb[i - j];
-                    float x = st[n][r] + sm.wpos[pbk];
-                    int tbk = 0;
-                    if (has_time) {
-                        tbk = time_bucket_dev(sm.ts_tile[il] - ((r < 2) ? ts_j0 : ts_j1), sm.thr, ntime);
-                        x += sm.wtime[tbk];
+                for (int r = 0; r < 4; ++r) {
+                    const int il = n * 8 + 2 * t + (r & 1), i = q0 + il;
+                    const int jl = warp * 16 + g + ((r < 2) ? 0 : 8), j = k0 + jl;
+                    const unsigned bk = sm.mb[il * ATT_MB_LD + jl];
+                    float av = 0.f, dsv = 0.f;
+                    if (bk != ATT_MASKED) {
+                        const int pbk = s_posb[i - j];
+                        const float x = st[n][r] + sm.wpos[pbk] + sm.wtime[bk];
+                        const float sg = sigmoidf_fast(x);
+                        av = x * sg;
+                        dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));
+                        my_hp[pbk * 32] += dsv;
+                        if (has_time) my_ht[bk * 32] += dsv;
                     }
-                    float sg = sigmoidf_fast(x);
-                    av = x * sg;
-                    dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));
-                    my_hp[pbk * 32] += dsv;
-                    if (has_time) my_ht[tbk * 32] += dsv;
+                    st[n][r] = av;
+                    dat[n][r] = dsv;
                 }
-                st[n][r] = av;
-                dat[n][r] = dsv;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
             }
         }
         uint32_t pf[4][4];
         att_pack_p(pf, st);
-        att_mma_nn<DH>(dv, pf, sm.tile[3], lane);  // dV += A^T dO
+        att_mma_nn<DH>(dv, pf, sm.tile[3], lane, kb0, 4);  // dV += A^T dO
         att_pack_p(pf, dat);
-        att_mma_nn<DH>(dk, pf, sm.tile[2], lane);  // dK += dS^T Q
+        att_mma_nn<DH>(dk, pf, sm.tile[2], lane, kb0, 4);  // dK += dS^T Q
     }
 
 #pragma unroll

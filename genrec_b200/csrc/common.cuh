@@ -44,11 +44,16 @@ GRB_DEVINL float warp_max(float v) {
 // Counter-based: keep(seed, site, idx) is a pure function, so the backward pass re-derives the forward mask
 // instead of storing it.  One 64-bit mix (splitmix64 finaliser) per element -> 32 uniform bits.
 GRB_DEVINL uint32_t rng_u32(uint64_t seed, uint32_t site, uint64_t idx) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    // 32-bit mixing (two rounds of a murmur3-style finaliser keyed by seed halves and the site): ~12 integer ops,
+    // no 64-bit multiplies.  idx < 2^40 in practice; its high bits are folded in.
+    uint32_t k0 = (uint32_t)seed ^ (site * 0x9E3779B1u), k1 = (uint32_t)(seed >> 32) + 0x7F4A7C15u;
+    uint32_t x = (uint32_t)idx ^ k0;
+    x += (uint32_t)(idx >> 32) * 0x85EBCA6Bu;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x += k1; x *= 0x846CA68Bu;
+    x ^= x >> 16; x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    return x;
 }
 struct Dropout {
     uint64_t seed;

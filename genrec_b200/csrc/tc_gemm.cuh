@@ -10,7 +10,8 @@
 // Persistent kernel, one CTA per SM, 192 threads:
 //   warp 0    : TMA producer (one elected lane)      - ring of TC_STAGES x (A 16 KB + B 16 KB)
 //   warp 1    : TMEM allocator + MMA issuer (one lane): 4 x tcgen05.mma (K = 16 each) per 64-wide k-block
-//   warps 2-5 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 = 32 rows of the 128 x 128 tile
+//   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 = 32 rows of the 128 x 128 tile and, by (w-2)/4, one
+//               64-column half of it (two warps per TMEM sub-partition so the element-wise work has 8 warps to run on)
 // Work item = (m tile, n tile, k split).  Split-K partial sums go out through an atomic epilogue.
 #pragma once
 #include <cuda.h>
@@ -19,9 +20,10 @@
 
 namespace grb {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 320;  // TMA, MMA, 8 epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB per operand per stage
-constexpr int TC_SMEM_BYTES = 2 * TC_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_STAGE_OUT_BYTES = 64 * 1024;   // epilogue staging: 2 x bf16 [128x128] or 1 x fp32 [128x128], 128B-swizzled boxes
+constexpr int TC_SMEM_BYTES = 2 * TC_STAGES * TC_TILE_BYTES + 2 * TC_STAGE_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_TMEM_COLS = 2 * TC_BN;           // two accumulators
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -54,6 +56,17 @@ GRB_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int
                  "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// shared -> global tile store (bulk async group); rows/cols outside the tensor map's extents are clipped by the hardware
+GRB_DEVINL void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+GRB_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+GRB_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+GRB_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+GRB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+GRB_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 GRB_DEVINL void tma_prefetch_desc(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -119,16 +132,23 @@ struct TcGemmShape {
     int kblocks_total, kblocks_per_split;
 };
 
-// Epilogue concept:  void prepare();   void operator()(int row, int col0, const float (&v)[32], int nvalid) const;
+// Epilogue concept:
+//   static constexpr int kOut;   0: the functor stores by itself (atomics / odd strides)      signature (row, col0, v, nvalid)
+//                                1: one bf16 output tile   2: two bf16 output tiles   3: one fp32 output tile
+//                                   -> signature (row, col0, v /*in: acc, out: primary*/, w /*out: secondary*/, nvalid); the kernel
+//                                      stages the tile in shared memory (128B swizzle) and writes it with TMA stores (tmC0 / tmC1).
+//   void prepare();
 template <int A_MN, int B_MN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmShape sh, Epi epi) {
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
+                   const __grid_constant__ CUtensorMap tmC1, TcGemmShape sh, Epi epi) {
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte aligned operand ring, then barriers
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;
     unsigned char* sB = base + TC_STAGES * TC_TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * TC_STAGES * TC_TILE_BYTES);
+    unsigned char* sOut0 = base + 2 * TC_STAGES * TC_TILE_BYTES;  // 2 x 64 KB staging (double-buffered), 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut0 + 2 * TC_STAGE_OUT_BYTES);
     uint64_t* full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]          MMA -> epilogue
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -227,8 +247,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
     } else {
-        // ===================================================================== epilogue (warps 2..5)
-        const int sub = warp & 3;  // TMEM sub-partition this warp may access: lanes 32*sub .. 32*sub+31
+        // ===================================================================== epilogue (warps 2..9)
+        const int sub = warp & 3;         // TMEM sub-partition this warp may access: lanes 32*sub .. 32*sub+31
+        const int chalf = (warp - 2) >> 2;  // which 64-column half of the tile this warp converts
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -236,21 +257,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int m0 = (tile / sh.num_n) * TC_BM, n0 = (tile % sh.num_n) * TC_BN;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m0 + sub * 32 + lane;
+            const int r = sub * 32 + lane;  // row inside the tile == TMEM lane
+            const int row = m0 + r;
+            unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
+            for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = n0 + c * 32;
                 const int nvalid = min(32, sh.N - col0);
-                if (row < sh.M && nvalid > 0) epi(row, col0, v, nvalid);
+                if constexpr (Epi::kOut == 0) {
+                    if (row < sh.M && nvalid > 0) epi(row, col0, v, nvalid);
+                } else {
+                    float w[32];
+                    if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid);
+                    if constexpr (Epi::kOut == 3) {
+                        // fp32: box c = [128 rows][32 cols] = 128 B rows, 16-byte chunk j stored at (j ^ (r & 7))
+                        unsigned char* dst = sOut + c * 16384 + r * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(dst + ((j ^ (r & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        // bf16: box h = [128 rows][64 cols]; this 32-column chunk covers 16-byte chunks (c&1)*4 .. +3 of box c>>1
+                        unsigned char* dst = sOut + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16(v[8 * j], v[8 * j + 1]); u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
+                        }
+                        if constexpr (Epi::kOut == 2) {
+                            unsigned char* dst1 = dst + 32768;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = pack_bf16(w[8 * j], w[8 * j + 1]); u.y = pack_bf16(w[8 * j + 2], w[8 * j + 3]);
+                                u.z = pack_bf16(w[8 * j + 4], w[8 * j + 5]); u.w = pack_bf16(w[8 * j + 6], w[8 * j + 7]);
+                                *reinterpret_cast<uint4*>(dst1 + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
+                            }
+                        }
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMA warp may start the next-but-one tile
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if constexpr (Epi::kOut != 0) {
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                epi_bar_sync();
+                if (warp == 2 && lane == 0) {
+                    if constexpr (Epi::kOut == 3) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (n0 + c * 32 < sh.N) tma_store_2d(&tmC0, sOut + c * 16384, n0 + c * 32, m0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (n0 + h * 64 < sh.N) {
+                                tma_store_2d(&tmC0, sOut + h * 16384, n0 + h * 64, m0);
+                                if constexpr (Epi::kOut == 2) tma_store_2d(&tmC1, sOut + 32768 + h * 16384, n0 + h * 64, m0);
+                            }
+                        }
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read1();  // the OTHER staging buffer (previous tile's group) has been read -> reusable
+                }
+                epi_bar_sync();
+            }
         }
     }
+    if (Epi::kOut != 0 && warp == 2 && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk stores
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -311,91 +389,89 @@ GRB_DEVINL void load_f32x32(const float* src, float (&v)[32], int nvalid) {
 // z = acc + bias -> bf16 ; act = dropout(ACT(z_rounded)) -> bf16      ACT 0: none (act_out unused), 1: silu, 2: relu
 template <int ACT>
 struct TcEpiBiasAct {
+    static constexpr int kOut = ACT == 0 ? 1 : 2;   // tmC0 = z, tmC1 = act
     const float* bias;
-    bf16* z_out;
-    bf16* act_out;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void operator()(int row, int col0, const float (&v)[32], int nvalid) const {
-        float z[32], a[32];
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&w)[32], int nvalid) const {
         const size_t o = (size_t)row * ld + col0;
+        float bb[32];
+        load_f32x32(bias + col0, bb, nvalid);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float zz = v[i] + (i < nvalid ? bias[col0 + i] : 0.f);
-            z[i] = zz;
+            float zz = v[i] + bb[i];
+            v[i] = zz;
             if (ACT != 0) {
                 float zr = bf16_round(zz);
                 float av = ACT == 1 ? siluf(zr) : fmaxf(zr, 0.f);
-                a[i] = drop.apply(av, o + i);
+                w[i] = drop.apply(av, o + i);
             }
         }
-        store_bf16x32(z_out + o, z, nvalid);
-        if (ACT != 0) store_bf16x32(act_out + o, a, nvalid);
     }
 };
 // y = res + dropout(acc + bias) (* row_scale) -> fp32
 struct TcEpiBiasResidual {
+    static constexpr int kOut = 3;
     const float* bias;
     const float* res;
-    float* out;
     const float* row_scale;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void operator()(int row, int col0, const float (&v)[32], int nvalid) const {
-        float r[32], y[32];
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
+        float r[32];
         const size_t o = (size_t)row * ld + col0;
         load_f32x32(res + o, r, nvalid);
         const float s = row_scale ? row_scale[row] : 1.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = (r[i] + drop.apply(v[i] + (i < nvalid ? bias[col0 + i] : 0.f), o + i)) * s;
-        store_f32x32(out + o, y, nvalid);
+        float bb[32];
+        load_f32x32(bias + col0, bb, nvalid);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (r[i] + drop.apply(v[i] + bb[i], o + i)) * s;
     }
 };
 // g = dropmask(acc) * ACT'(z) -> bf16
 template <int ACT>
 struct TcEpiDAct {
+    static constexpr int kOut = 1;
     const bf16* z;
-    bf16* out;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void operator()(int row, int col0, const float (&v)[32], int nvalid) const {
-        float zz[32], g[32];
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
+        float zz[32];
         const size_t o = (size_t)row * ld + col0;
         load_bf16x32(z + o, zz, nvalid);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             float d = ACT == 1 ? dsiluf(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
-            g[i] = drop.apply(v[i], o + i) * d;
+            v[i] = drop.apply(v[i], o + i) * d;
         }
-        store_bf16x32(out + o, g, nvalid);
     }
 };
 // out = scale * acc (+ res) -> fp32
 struct TcEpiF32 {
-    float* out;
+    static constexpr int kOut = 3;
     const float* res;
     int ld;
     float scale;
     GRB_DEVINL void prepare() {}
-    GRB_DEVINL void operator()(int row, int col0, const float (&v)[32], int nvalid) const {
-        float y[32];
-        const size_t o = (size_t)row * ld + col0;
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
         if (res) {
-            load_f32x32(res + o, y, nvalid);
+            float y[32];
+            load_f32x32(res + (size_t)row * ld + col0, y, nvalid);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] += v[i] * scale;
+            for (int i = 0; i < 32; ++i) v[i] = y[i] + v[i] * scale;
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = v[i] * scale;
+            for (int i = 0; i < 32; ++i) v[i] *= scale;
         }
-        store_f32x32(out + o, y, nvalid);
     }
 };
 // out += scale * acc (split-K partial sums, weight gradients)
 struct TcEpiAtomicF32 {
+    static constexpr int kOut = 0;
     float* out;
     int ld;
     float scale;
@@ -409,15 +485,13 @@ struct TcEpiAtomicF32 {
 };
 // plain bf16 store
 struct TcEpiBf16 {
-    bf16* out;
-    int ld;
+    static constexpr int kOut = 1;
     GRB_DEVINL void prepare() {}
-    GRB_DEVINL void operator()(int row, int col0, const float (&v)[32], int nvalid) const {
-        store_bf16x32(out + (size_t)row * ld + col0, v, nvalid);
-    }
+    GRB_DEVINL void operator()(int, int, float (&)[32], float (&)[32], int) const {}
 };
 // plain fp32 store, arbitrary leading dimension
 struct TcEpiF32Plain {
+    static constexpr int kOut = 0;
     float* out;
     int ld;
     GRB_DEVINL void prepare() {}
@@ -442,25 +516,42 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
-// 2-D bf16 row-major tensor [rows][cols] with leading dimension ld (elements); box = {box_cols (inner), box_rows}
-inline bool make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+// 2-D row-major tensor [rows][cols] with leading dimension ld (elements); box = {box_cols (inner, 128 bytes), box_rows}
+inline bool make_tmap(CUtensorMap* m, const void* base, bool fp32, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return false;
+    const uint64_t esz = fp32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * esz) & 15)) return false;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * esz};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+    return make_tmap(m, base, false, rows, cols, ld, box_cols, box_rows);
 }
 
 // A: A_MN == 0 -> [M][K] ld=lda ; A_MN == 1 -> [K][M] ld=lda.   Same for B with N.
+// out0 / out1: output tensors [M][N] with leading dimension ldo (bf16 for kOut 1/2, fp32 for kOut 3); unused for kOut 0.
 template <int A_MN, int B_MN, class Epi>
 inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, int K, int lda, int ldb, int splits, const Epi& epi,
-                                  int num_sms, cudaStream_t st) {
-    CUtensorMap tmA, tmB;
+                                  void* out0, void* out1, int ldo, int num_sms, cudaStream_t st) {
+    CUtensorMap tmA, tmB, tmC0, tmC1;
     bool ok = A_MN == 0 ? make_tmap_bf16(&tmA, A, M, K, lda, TC_BK, TC_BM) : make_tmap_bf16(&tmA, A, K, M, lda, 64, TC_BK);
     ok = ok && (B_MN == 0 ? make_tmap_bf16(&tmB, B, N, K, ldb, TC_BK, TC_BN) : make_tmap_bf16(&tmB, B, K, N, ldb, 64, TC_BK));
+    if (Epi::kOut == 0) {
+        tmC0 = tmA; tmC1 = tmA;
+    } else if (Epi::kOut == 3) {
+        ok = ok && make_tmap(&tmC0, out0, true, M, N, ldo, 32, TC_BM);
+        tmC1 = tmC0;
+    } else {
+        ok = ok && make_tmap(&tmC0, out0, false, M, N, ldo, 64, TC_BM);
+        if (Epi::kOut == 2) ok = ok && make_tmap(&tmC1, out1, false, M, N, ldo, 64, TC_BM);
+        else tmC1 = tmC0;
+    }
     if (!ok) return cudaErrorInvalidValue;
     TcGemmShape sh;
     sh.M = M; sh.N = N; sh.K = K;
@@ -480,7 +571,7 @@ inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, in
     }
     int work = sh.num_m * sh.num_n * sh.splits;
     int grid = work < num_sms ? work : num_sms;
-    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmB, sh, epi);
+    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmB, tmC0, tmC1, sh, epi);
     return cudaGetLastError();
 }
 

@@ -34,17 +34,25 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 
 
 class SeqMeta:
-    """Per-batch sequence metadata shared by all layers of one forward: pad flags, timestamps, bucket tables."""
+    """Per-batch sequence metadata shared by all layers of one forward.  Builds the [B, L, ld] mask/bucket byte matrix
+    once (grb_hstu_mask_bucket) from the pad flags and timestamps."""
 
     def __init__(self, pad_u8: torch.Tensor, timestamps: Optional[torch.Tensor], pos_bucket: torch.Tensor,
-                 time_thr: torch.Tensor):
-        self.pad = pad_u8
-        self.timestamps = timestamps
+                 time_thr: torch.Tensor, num_time_buckets: int = 64):
+        require_cuda(pad_u8)
+        B, L = pad_u8.shape
+        self.pad = pad_u8.contiguous()
+        self.timestamps = timestamps.contiguous() if timestamps is not None else None
         self.pos_bucket = pos_bucket
-        self.time_thr = time_thr
+        self.ld = (L + 15) // 16 * 16
+        self.mask_bucket = torch.empty(B, L, self.ld, dtype=torch.uint8, device=pad_u8.device)
+        nt = num_time_buckets if self.timestamps is not None else 0
+        check(_lib.load().grb_hstu_mask_bucket(ptr(self.timestamps), ptr(self.pad), ptr(time_thr), B, L, nt, ptr(self.mask_bucket),
+                                               self.ld, stream_ptr(pad_u8.device)))
+        _lib.count_launches(1)
 
     def struct(self) -> HstuSeq:
-        return HstuSeq(ptr(self.pad), ptr(self.timestamps), ptr(self.pos_bucket), ptr(self.time_thr))
+        return HstuSeq(ptr(self.mask_bucket), self.ld, 1 if self.timestamps is not None else 0, ptr(self.pos_bucket))
 
 
 def _dims(B, L, D, H, npos, ntime, p, seed, seed_dev, layer) -> HstuDims:

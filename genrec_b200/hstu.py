@@ -194,7 +194,8 @@ class HSTULayer(nn.Module):
             B, L, _ = x.shape
             ts = timestamps.contiguous() if (timestamps is not None and self.use_temporal_bias) else None
             _meta = Fn.SeqMeta(padding_mask.to(torch.uint8).contiguous(), ts,
-                               self.position_bias.bucket_of_delta(L, x.device), _thresholds_on(x.device))
+                               self.position_bias.bucket_of_delta(L, x.device), _thresholds_on(x.device),
+                               self.temporal_bias.num_buckets if self.use_temporal_bias else 0)
         return self._run(x, _meta, _seed, _seed_dev)
 
 
@@ -274,7 +275,8 @@ class HSTU(nn.Module):
         if len(self.layers):
             ts = timestamps.contiguous() if (timestamps is not None and self.use_temporal_bias) else None
             meta = Fn.SeqMeta(pad, ts, self.layers[0].position_bias.bucket_of_delta(L, input_ids.device),
-                              _thresholds_on(input_ids.device))
+                              _thresholds_on(input_ids.device),
+                              self.layers[0].temporal_bias.num_buckets if self.use_temporal_bias else 0)
             for layer in self.layers:
                 layer._bf16_provider = self._bf16_provider
                 x = layer(x, None, None, timestamps, _meta=meta, _seed=seed, _seed_dev=seed_dev)

@@ -69,11 +69,19 @@ typedef struct {             /* fp32, same shapes as the parameters, accumulated
 } grb_hstu_layer_grads;
 
 typedef struct {
-    const uint8_t* pad;         /* [B, L] 1 = padded key (input_ids == 0, hstu.py:124) */
-    const int64_t* timestamps;  /* [B, L] or NULL (hstu.py:251) */
+    const uint8_t* mask_bucket; /* [B, L, ld_mask] from grb_hstu_mask_bucket(): temporal bucket of |ts_i - ts_j|, 255 = masked cell */
+    int ld_mask;                /* row pitch in bytes: a multiple of 16, >= L */
+    int has_time;               /* 0: timestamps were None -> the temporal term is dropped (hstu.py:251) */
     const uint8_t* pos_bucket;  /* [L] bucket of delta = i - j >= 0, precomputed by the host from the reference formula */
-    const int64_t* time_thr;    /* [65] thr[k] = smallest |dt| whose reference bucket is >= k ; thr[64] = INT64_MAX */
 } grb_hstu_seq;
+
+/* Per-batch integer preprocessing shared by all layers / heads / passes (replaces the index arithmetic of
+ * TemporalBias._temporal_bucket, hstu.py:368-384, and the two masked_fill's, :256-259):
+ *   out[b,i,j] = (j <= i && !pad[b,j]) ? clamp(trunc(log_f32(max(1,|ts_i - ts_j|)) / 0.693), 0, ntime-1) : 255
+ * evaluated exactly through integer thresholds: time_thr[k] = smallest |dt| whose reference bucket is >= k (k < 64),
+ * time_thr[64] = INT64_MAX.  timestamps may be NULL (bucket 0 everywhere).  pad: [B, L], 1 = input_ids == 0. */
+int grb_hstu_mask_bucket(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, int B, int L, int ntime,
+                         uint8_t* out, int ld_mask, void* stream);
 
 size_t grb_hstu_layer_saved_bytes(const grb_hstu_dims* d);
 size_t grb_hstu_layer_workspace_bytes(const grb_hstu_dims* d);
