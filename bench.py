@@ -321,7 +321,8 @@ def block_roofline(model, B, L, dev, K):
     import genrec_b200.functional as Fn
     from genrec_b200.hstu import _thresholds_on
     pad = (ids == 0).to(torch.uint8)
-    meta = Fn.SeqMeta(pad, ts, model.layers[0].position_bias.bucket_of_delta(L, dev), _thresholds_on(dev), 64)
+    meta = Fn.SeqMeta(pad, ts, model.layers[0].position_bias.bucket_of_delta(L, dev), _thresholds_on(dev), 64, 32,
+                      model.layers[0].position_bias.uniform_of(L, dev))
     seed, seed_dev = model._seeds(dev)
 
     def fb():

@@ -34,7 +34,7 @@ class HstuLayerGrads(C.Structure):
 
 
 class HstuSeq(C.Structure):
-    _fields_ = [("mask_bucket", c_void_p), ("ld_mask", c_int), ("has_time", c_int), ("pos_bucket", c_void_p)]
+    _fields_ = [("bias_index", c_void_p), ("ld_index", c_int), ("has_time", c_int), ("pos_uniform", c_int), ("pos_bucket0", c_int)]
 
 
 class SasrecDims(C.Structure):
@@ -53,7 +53,7 @@ SIGNATURES = {
     "grb_hstu_layer_forward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p, c_void_p]),
     "grb_hstu_layer_backward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p,
                                         P(HstuLayerGrads), c_void_p, c_void_p]),
-    "grb_hstu_mask_bucket": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "grb_hstu_bias_index": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "grb_embed_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                   c_float, c_u64, c_void_p, c_void_p]),
     "grb_embed_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float,

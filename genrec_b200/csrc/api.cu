@@ -222,13 +222,16 @@ HstuAttnArgs make_attn_args(const grb_hstu_dims* d, const grb_hstu_layer_params*
     a.q = sv.P + 2 * D; a.k = sv.P + 3 * D; a.v = sv.P + D;
     a.ldq = a.ldk = a.ldv = 4 * D;
     a.B = d->B; a.L = d->L; a.H = d->H;
-    a.bias.wpos = p->pos_table;
-    a.bias.pos_bucket = s->pos_bucket;
+    // uniform position buckets (the reference's behaviour) collapse to ONE effective bucket: the index matrix was built with
+    // npos = 1, the tables shrink to 65 entries and the pointers are offset to the single live row of the [npos, H] table
+    a.bias.wpos = p->pos_table + (s->pos_uniform ? (size_t)s->pos_bucket0 * d->H : 0);
     const bool has_time = p->time_table != nullptr && s->has_time && d->ntime > 0;
     a.bias.wtime = has_time ? p->time_table : nullptr;
-    a.bias.mask_bucket = s->mask_bucket;
-    a.bias.ldmb = s->ld_mask;
-    a.bias.npos = d->npos;
+    a.bias.bias_index = s->bias_index;
+    a.bias.ldix = s->ld_index;
+    a.bias.pos_uniform = s->pos_uniform;
+    a.bias.pos_bucket0 = 0;
+    a.bias.npos = s->pos_uniform ? 1 : d->npos;
     a.bias.ntime = has_time ? d->ntime : 0;
     a.o = sv.O; a.ldo = D;
     return a;
@@ -236,7 +239,7 @@ HstuAttnArgs make_attn_args(const grb_hstu_dims* d, const grb_hstu_layer_params*
 
 template <int DH>
 int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
-    size_t smem = sizeof(AttSmem<DH>) + align_up(a.L, 16);
+    size_t smem = sizeof(AttSmem<DH>) + align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);
     GRB_TRY(set_smem(hstu_attn_fwd_kernel<DH>, smem));
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
     hstu_attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(a);
@@ -246,12 +249,12 @@ int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
 template <int DH>
 int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
-    size_t posb = align_up(a.L, 16);
+    size_t posb = align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);  // combined bias table
     size_t smem_q = sizeof(AttSmem<DH>) + posb;
     GRB_TRY(set_smem(hstu_attn_bwd_dq_kernel<DH>, smem_q));
     hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
     GRB_CUDA(cudaGetLastError());
-    size_t smem_k = sizeof(AttSmem<DH>) + posb + (size_t)4 * (a.bias.ntime + a.bias.npos) * 32 * sizeof(float);
+    size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos)) * 32 * sizeof(float);
     GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
     hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, (int)posb);
     GRB_CUDA(cudaGetLastError());
@@ -326,8 +329,8 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
     GRB_REQUIRE(p && s && x && y && saved, "null argument");
     GRB_REQUIRE(p->proj_w && p->proj_b && p->pos_table && p->ln1_g && p->ln1_b && p->ffn1_w && p->ffn1_b && p->ffn2_w &&
                     p->ffn2_b && p->ln2_g && p->ln2_b, "null parameter pointer");
-    GRB_REQUIRE(s->mask_bucket && s->pos_bucket, "null sequence metadata");
-    GRB_REQUIRE(s->ld_mask >= d->L && s->ld_mask % 16 == 0 && aligned16(s->mask_bucket), "mask_bucket pitch must be a multiple of 16 and >= L");
+    GRB_REQUIRE(s->bias_index, "null sequence metadata");
+    GRB_REQUIRE(s->ld_index >= d->L && s->ld_index % 8 == 0 && aligned16(s->bias_index), "bias_index pitch must be a multiple of 8 and >= L");
     GRB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(saved) && aligned16(p->proj_w) && aligned16(p->ffn1_w) && aligned16(p->ffn2_w),
                 "buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -411,7 +414,7 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
         a.d_o = w.dO; a.lddo = D;
         a.zq = sv.zp + 2 * D; a.zk = sv.zp + 3 * D; a.zv = sv.zp + D; a.ldz = 4 * D;
         a.dq = w.dzp + 2 * D; a.dk = w.dzp + 3 * D; a.dv = w.dzp + D; a.lddq = 4 * D;
-        a.dwpos = g->pos_table;
+        a.dwpos = g->pos_table + (s->pos_uniform ? (size_t)s->pos_bucket0 * d->H : 0);
         a.dwtime = g->time_table;
         GRB_REQUIRE(a.bias.wtime == nullptr || g->time_table != nullptr, "time_table gradient pointer is null");
         if (D / d->H == 32) GRB_TRY(launch_hstu_attn_bwd<32>(a, st));
@@ -436,15 +439,16 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     return 0;
 }
 
-int grb_hstu_mask_bucket(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, int B, int L, int ntime, uint8_t* out,
-                         int ld_mask, void* stream) {
-    GRB_REQUIRE(pad && time_thr && out, "null argument");
+int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, const uint8_t* pos_bucket, int B, int L,
+                        int npos, int ntime, uint16_t* out, int ld_index, void* stream) {
+    GRB_REQUIRE(pad && time_thr && pos_bucket && out, "null argument");
     GRB_REQUIRE(B > 0 && L > 0 && B <= 65535 && L <= 65535, "bad shape B=%d L=%d", B, L);
-    GRB_REQUIRE(ld_mask >= L && ld_mask % 16 == 0, "ld_mask must be a multiple of 16 and >= L");
-    GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS, "num_time_buckets out of range");
-    dim3 grid((ld_mask + 255) / 256, L, B);
-    hstu_mask_bucket_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(timestamps), pad,
-                                                                                  reinterpret_cast<const long long*>(time_thr), L, ld_mask, ntime, out);
+    GRB_REQUIRE(ld_index >= L && ld_index % 8 == 0, "ld_index must be a multiple of 8 and >= L");
+    GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS && npos >= 1 && npos <= ATT_MAX_BUCKETS, "bucket counts out of range");
+    dim3 grid((ld_index + 255) / 256, L, B);
+    hstu_bias_index_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(timestamps), pad,
+                                                                                 reinterpret_cast<const long long*>(time_thr), pos_bucket, L,
+                                                                                 ld_index, npos, ntime, out);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -5,14 +5,18 @@
 //   A          = valid ? silu(S) : 0          O = A V
 // (reference: genrec/models/hstu.py:244-267).  No [L,L] fp tensor ever reaches HBM.
 //
-// All integer work is hoisted out of the per-head / per-layer kernels: `hstu_mask_bucket_kernel` runs ONCE per batch and
-// writes one byte per (b, i, j): the temporal bucket of |ts_i - ts_j| (integer-threshold form of the reference's
-// fp32 log / 0.693 expression), or 255 when the cell is masked (j > i, padded key).  The 5 MB byte matrix (cfg-2) stays
-// L2-resident and is re-used by every head of every layer, forward and backward (4 layers x 3 kernels x 4 heads).
+// All integer work is hoisted out of the per-head / per-layer kernels: `hstu_bias_index_kernel` runs ONCE per batch and
+// writes one uint16 per (b, i, j):  pb(i-j) * 64 + tb(|ts_i - ts_j|)  (tb = integer-threshold form of the reference's
+// fp32 log / 0.693 expression), or the sentinel npos*64 when the cell is masked (j > i, padded key).  Each attention CTA
+// builds, for its head, the table  wcomb[pb*64 + tb] = Wpos[pb,h] + Wtime[tb,h]  in shared memory with
+// wcomb[sentinel] = -30000: silu(-30000) and silu'(-30000) are exactly 0 in fp32, so masking costs no instruction.
+// The per-element work is then: one 16-bit index load, one table load, one add, the SiLU.
+// The 10 MB index matrix (cfg-2) stays L2-resident and is shared by every head of every layer, forward and backward.
 //
 // Layout: Q/K/V/dO/O are row-major [T = B*L, ld] bf16 with head h at columns h*DH .. h*DH+DH-1.
-// One CTA = 4 warps = 64 query rows (fwd, dQ) or 64 key rows (dK/dV); KV (resp. Q) tiles of 64 stream through smem.
-// Warps whose rows lie beyond L, and 8-key column blocks above the causal diagonal, are skipped (warp-uniform branches).
+// One CTA = 4 warps = 64 query rows (fwd, dQ) or 64 key rows (dK/dV); the other operand streams through shared memory
+// in double-buffered 64-row tiles (cp.async).  Warps whose rows lie beyond L and 8-wide blocks above the causal diagonal
+// are skipped (warp-uniform branches).
 #pragma once
 #include "common.cuh"
 
@@ -21,16 +25,17 @@ namespace grb {
 constexpr int ATT_BLK = 64;       // rows per CTA and per streamed tile
 constexpr int ATT_THREADS = 128;  // 4 warps x 16 rows
 constexpr int ATT_MAX_BUCKETS = 64;
-constexpr int ATT_MB_LD = ATT_BLK + 16;  // padded row (bytes) of the mask/bucket tile in smem
-constexpr unsigned ATT_MASKED = 255u;
+constexpr int ATT_IX_LD = ATT_BLK + 8;  // padded row (uint16 elements) of the index tile in smem: 144 B, conflict-free
+constexpr float ATT_MASK_BIAS = -30000.f;
 
 struct HstuBiasArgs {
     const float* wpos;           // [npos, H]
-    const uint8_t* pos_bucket;   // [L]   bucket of delta = i - j >= 0  (host: reference bucketing of clamp(j - i, 0) -> all 0)
     const float* wtime;          // [ntime, H] or null
-    const uint8_t* mask_bucket;  // [B, L, ldmb]  temporal bucket (0 if no temporal bias) or 255 = masked
-    int ldmb;
+    const uint16_t* bias_index;  // [B, L, ldix]
+    int ldix;                    // elements, multiple of 8
     int npos, ntime;
+    int pos_uniform;             // 1: every delta in [0, L) maps to pos bucket `pos_bucket0` (the reference's degenerate case)
+    int pos_bucket0;
 };
 
 struct HstuAttnArgs {
@@ -56,29 +61,32 @@ GRB_DEVINL int time_bucket_dev(long long dt, const long long* thr, int ntime) {
     return min(b, ntime - 1);
 }
 
-// out[b, i, j] = (j <= i && !pad[b, j]) ? bucket(|ts[b,i] - ts[b,j]|) : 255        grid (ceil(ld/256), L, B)
-__global__ void __launch_bounds__(256) hstu_mask_bucket_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad,
-                                                              const long long* __restrict__ thr_g, int L, int ld, int ntime,
-                                                              uint8_t* __restrict__ out) {
+// out[b, i, j] = (j <= i && !pad[b, j]) ? pos_bucket[i - j] * 64 + bucket(|ts[b,i] - ts[b,j]|) : npos * 64      grid (ceil(ld/256), L, B)
+__global__ void __launch_bounds__(256) hstu_bias_index_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad,
+                                                             const long long* __restrict__ thr_g, const uint8_t* __restrict__ pos_bucket,
+                                                             int L, int ld, int npos, int ntime, uint16_t* __restrict__ out) {
     __shared__ long long thr[ATT_MAX_BUCKETS + 1];
     for (int i = threadIdx.x; i <= ATT_MAX_BUCKETS; i += 256) thr[i] = thr_g[i];
     __syncthreads();
     const int b = blockIdx.z, i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
     if (j >= ld) return;
     const size_t row = (size_t)b * L;
-    unsigned v = ATT_MASKED;
-    if (j <= i && j < L && pad[row + j] == 0) v = (ts != nullptr && ntime > 0) ? (unsigned)time_bucket_dev(ts[row + i] - ts[row + j], thr, ntime) : 0u;
-    out[(row + i) * ld + j] = (uint8_t)v;
+    unsigned v = (unsigned)npos * 64u;
+    if (j <= i && j < L && pad[row + j] == 0) {
+        const unsigned tb = (ts != nullptr && ntime > 0) ? (unsigned)time_bucket_dev(ts[row + i] - ts[row + j], thr, ntime) : 0u;
+        v = (unsigned)pos_bucket[i - j] * 64u + tb;
+    }
+    out[(row + i) * ld + j] = (uint16_t)v;
 }
 
 template <int DH>
 struct AttSmem {
     static constexpr int LD = DH + 8;
-    bf16 tile[4][ATT_BLK * LD];  // roles differ per kernel
-    float wpos[ATT_MAX_BUCKETS];
-    float wtime[ATT_MAX_BUCKETS];
-    uint8_t mb[ATT_BLK * ATT_MB_LD];  // [query row][key col] bytes of the current (q tile, kv tile) pair
+    bf16 fixed[2][ATT_BLK * LD];      // the CTA's own rows (Q [+ dO]  or  K, V)
+    bf16 stream[2][2][ATT_BLK * LD];  // [buffer][operand] streamed tiles
+    uint16_t ix[2][ATT_BLK * ATT_IX_LD];  // [buffer] index tile: [query row][key col]
 };
+// dynamic tail after AttSmem: float wcomb[npos*64 + 1] ; (dK/dV only) lane-private histograms
 
 // cooperative 64 x DH tile load (rows row0.. of one batch element, zero-filled beyond L)
 template <int DH>
@@ -92,22 +100,26 @@ GRB_DEVINL void att_load_tile(bf16* s, const bf16* g, int ld, long long tok0, in
         cp_async16(s + r * LD + kc, src, ok ? 16 : 0);
     }
 }
-// 64 x 64 byte tile of the mask/bucket matrix: rows q0.., cols k0.. (ldmb is a multiple of 16 and >= the padded width)
-GRB_DEVINL void att_load_mb(uint8_t* s, const uint8_t* g, int ldmb, long long tok0, int q0, int k0, int L, int tid) {
-    for (int c = tid; c < ATT_BLK * 4; c += ATT_THREADS) {
-        int r = c >> 2, kc = (c & 3) * 16;
-        bool ok = (q0 + r) < L && (k0 + kc) < ldmb;
-        if (ok) cp_async16(s + r * ATT_MB_LD + kc, g + (size_t)(tok0 + q0 + r) * ldmb + k0 + kc, 16);
-        else *reinterpret_cast<uint4*>(s + r * ATT_MB_LD + kc) = make_uint4(~0u, ~0u, ~0u, ~0u);  // out of range == masked
+// 64 x 64 uint16 tile of the index matrix: rows q0.., cols k0.. ; everything out of range reads as `sentinel`
+GRB_DEVINL void att_load_ix(uint16_t* s, const uint16_t* g, int ldix, long long tok0, int q0, int k0, int L, unsigned sentinel, int tid) {
+    const unsigned s2 = sentinel | (sentinel << 16);
+    for (int c = tid; c < ATT_BLK * 8; c += ATT_THREADS) {
+        int r = c >> 3, kc = (c & 7) * 8;
+        bool ok = (q0 + r) < L && (k0 + kc) < ldix;
+        if (ok) cp_async16(s + r * ATT_IX_LD + kc, g + (size_t)(tok0 + q0 + r) * ldix + k0 + kc, 16);
+        else *reinterpret_cast<uint4*>(s + r * ATT_IX_LD + kc) = make_uint4(s2, s2, s2, s2);
     }
 }
-
-template <int DH>
-GRB_DEVINL void att_load_bias_tables(AttSmem<DH>& sm, const HstuBiasArgs& b, int h, int H, int tid) {
-    for (int i = tid; i < ATT_MAX_BUCKETS; i += ATT_THREADS) {
-        sm.wpos[i] = i < b.npos ? b.wpos[i * H + h] : 0.f;
-        sm.wtime[i] = (b.wtime && i < b.ntime) ? b.wtime[i * H + h] : 0.f;
+// wcomb[pb*64 + tb] = Wpos[pb,h] + Wtime[tb,h] ; wcomb[npos*64] = mask
+GRB_DEVINL void att_build_table(float* wcomb, const HstuBiasArgs& b, int h, int H, int tid) {
+    const int n = b.npos * 64;
+    for (int i = tid; i < n; i += ATT_THREADS) {
+        const int pb = i >> 6, tb = i & 63;
+        float v = b.wpos[pb * H + h];
+        if (b.wtime && tb < b.ntime) v += b.wtime[tb * H + h];
+        wcomb[i] = v;
     }
+    if (tid == 0) wcomb[n] = ATT_MASK_BIAS;
 }
 
 // A-operand fragments of a 16 x DH slab (rows wrow..wrow+15 of an smem tile)
@@ -167,29 +179,31 @@ GRB_DEVINL void att_pack_p(uint32_t (&pf)[4][4], const float (&s)[8][4]) {
 }
 
 // ============================================================================================ forward
-// tile roles: 0 = Q, 1 = K, 2 = V
+// fixed[0] = Q ; stream[buf] = {K, V}
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs a) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
-    uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);  // [L]
+    float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH>));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
+    const unsigned sentinel = (unsigned)a.bias.npos * 64u;
 
-    att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
-    att_load_tile<DH>(sm.tile[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
+    att_build_table(wcomb, a.bias, h, a.H, tid);
+    att_load_tile<DH>(sm.fixed[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
+    auto load_stream = [&](int kt, int buf) {
+        att_load_tile<DH>(sm.stream[buf][0], a.k, a.ldk, tok0, kt * ATT_BLK, L, h * DH, tid);
+        att_load_tile<DH>(sm.stream[buf][1], a.v, a.ldv, tok0, kt * ATT_BLK, L, h * DH, tid);
+        att_load_ix(sm.ix[buf], a.bias.bias_index, a.bias.ldix, tok0, q0, kt * ATT_BLK, L, sentinel, tid);
+    };
+    load_stream(0, 0);
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
 
-    uint32_t qf[DH / 16][4];
-    att_load_afrag<DH>(qf, sm.tile[0], warp * 16, lane);
     const int i0 = q0 + warp * 16 + g, i1 = i0 + 8;
     const bool warp_live = q0 + warp * 16 < L;  // warp-uniform
-
+    uint32_t qf[DH / 16][4];
     float o[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n)
@@ -197,47 +211,42 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
         for (int r = 0; r < 4; ++r) o[n][r] = 0.f;
 
     for (int kt = 0; kt <= qt; ++kt) {
-        const int k0 = kt * ATT_BLK;
-        __syncthreads();  // previous tile fully consumed
-        att_load_tile<DH>(sm.tile[1], a.k, a.ldk, tok0, k0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[2], a.v, a.ldv, tok0, k0, L, h * DH, tid);
-        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        if (!warp_live) continue;
-        // 8-key blocks that intersect the causal triangle of this warp's 16 rows (diagonal tile only)
-        const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
-        const int npairs = (nblk + 1) >> 1;
-
-        float s[8][4];
+        const int buf = kt & 1;
+        if (kt < qt) {
+            load_stream(kt + 1, buf ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // tile kt (and, first time, Q + table) visible to everyone
+        if (kt == 0) att_load_afrag<DH>(qf, sm.fixed[0], warp * 16, lane);
+        if (warp_live) {
+            const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;  // 8-key blocks intersecting this warp's causal triangle
+            const int npairs = (nblk + 1) >> 1;
+            float s[8][4];
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+            for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) s[n][r] = 0.f;
-        att_mma_nt<DH>(s, qf, sm.tile[1], lane, npairs);
-
+                for (int r = 0; r < 4; ++r) s[n][r] = 0.f;
+            att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);
+            const uint16_t* ix = sm.ix[buf];
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (n < 2 * npairs) {
+            for (int n = 0; n < 8; ++n) {
+                if (n < 2 * npairs) {
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int il = warp * 16 + g + 8 * hf, i = q0 + il;
-                    const int jl = n * 8 + 2 * t, j = k0 + jl;
-                    const unsigned mb2 = *reinterpret_cast<const uint16_t*>(sm.mb + il * ATT_MB_LD + jl);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const unsigned bk = (mb2 >> (8 * e)) & 0xffu;
-                        float val = 0.f;
-                        if (bk != ATT_MASKED) val = siluf(s[n][2 * hf + e] + sm.wpos[s_posb[i - j - e]] + sm.wtime[bk]);
-                        s[n][2 * hf + e] = val;
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
+                        s[n][2 * hf] = siluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);
+                        s[n][2 * hf + 1] = siluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
                     }
                 }
             }
+            uint32_t pf[4][4];
+            att_pack_p(pf, s);
+            att_mma_nn<DH>(o, pf, sm.stream[buf][1], lane, 0, npairs);
         }
-        uint32_t pf[4][4];
-        att_pack_p(pf, s);
-        att_mma_nn<DH>(o, pf, sm.tile[2], lane, 0, npairs);
+        __syncthreads();  // everyone done with buffer `buf` before it is refilled two iterations later
     }
 
 #pragma unroll
@@ -249,30 +258,32 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
 }
 
 // ============================================================================================ backward: dQ
-// tile roles: 0 = Q, 1 = K, 2 = V, 3 = dO
+// fixed = {Q, dO} ; stream[buf] = {K, V}
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnArgs a) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
-    uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);
+    float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH>));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
+    const unsigned sentinel = (unsigned)a.bias.npos * 64u;
 
-    att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
-    att_load_tile<DH>(sm.tile[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
-    att_load_tile<DH>(sm.tile[3], a.d_o, a.lddo, tok0, q0, L, h * DH, tid);
+    att_build_table(wcomb, a.bias, h, a.H, tid);
+    att_load_tile<DH>(sm.fixed[0], a.q, a.ldq, tok0, q0, L, h * DH, tid);
+    att_load_tile<DH>(sm.fixed[1], a.d_o, a.lddo, tok0, q0, L, h * DH, tid);
+    auto load_stream = [&](int kt, int buf) {
+        att_load_tile<DH>(sm.stream[buf][0], a.k, a.ldk, tok0, kt * ATT_BLK, L, h * DH, tid);
+        att_load_tile<DH>(sm.stream[buf][1], a.v, a.ldv, tok0, kt * ATT_BLK, L, h * DH, tid);
+        att_load_ix(sm.ix[buf], a.bias.bias_index, a.bias.ldix, tok0, q0, kt * ATT_BLK, L, sentinel, tid);
+    };
+    load_stream(0, 0);
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
 
-    uint32_t qf[DH / 16][4], dof[DH / 16][4];
-    att_load_afrag<DH>(qf, sm.tile[0], warp * 16, lane);
-    att_load_afrag<DH>(dof, sm.tile[3], warp * 16, lane);
     const int i0 = q0 + warp * 16 + g, i1 = i0 + 8;
     const bool warp_live = q0 + warp * 16 < L;
+    uint32_t qf[DH / 16][4], dof[DH / 16][4];
     float dq[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n)
@@ -280,47 +291,46 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
         for (int r = 0; r < 4; ++r) dq[n][r] = 0.f;
 
     for (int kt = 0; kt <= qt; ++kt) {
-        const int k0 = kt * ATT_BLK;
+        const int buf = kt & 1;
+        if (kt < qt) {
+            load_stream(kt + 1, buf ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        att_load_tile<DH>(sm.tile[1], a.k, a.ldk, tok0, k0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[2], a.v, a.ldv, tok0, k0, L, h * DH, tid);
-        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        if (!warp_live) continue;
-        const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
-        const int npairs = (nblk + 1) >> 1;
-
-        float s[8][4], da[8][4];
+        if (kt == 0) {
+            att_load_afrag<DH>(qf, sm.fixed[0], warp * 16, lane);
+            att_load_afrag<DH>(dof, sm.fixed[1], warp * 16, lane);
+        }
+        if (warp_live) {
+            const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
+            const int npairs = (nblk + 1) >> 1;
+            float s[8][4], da[8][4];
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+            for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) s[n][r] = 0.f, da[n][r] = 0.f;
-        att_mma_nt<DH>(s, qf, sm.tile[1], lane, npairs);    // S  = Q K^T
-        att_mma_nt<DH>(da, dof, sm.tile[2], lane, npairs);  // dA = dO V^T
+                for (int r = 0; r < 4; ++r) s[n][r] = 0.f, da[n][r] = 0.f;
+            att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);    // S  = Q K^T
+            att_mma_nt<DH>(da, dof, sm.stream[buf][1], lane, npairs);  // dA = dO V^T
+            const uint16_t* ix = sm.ix[buf];
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (n < 2 * npairs) {
+            for (int n = 0; n < 8; ++n) {
+                if (n < 2 * npairs) {
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int il = warp * 16 + g + 8 * hf, i = q0 + il;
-                    const int jl = n * 8 + 2 * t, j = k0 + jl;
-                    const unsigned mb2 = *reinterpret_cast<const uint16_t*>(sm.mb + il * ATT_MB_LD + jl);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const unsigned bk = (mb2 >> (8 * e)) & 0xffu;
-                        float val = 0.f;
-                        if (bk != ATT_MASKED)
-                            val = da[n][2 * hf + e] * dsiluf(s[n][2 * hf + e] + sm.wpos[s_posb[i - j - e]] + sm.wtime[bk]);
-                        s[n][2 * hf + e] = val;  // dS
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
+                        s[n][2 * hf] = da[n][2 * hf] * dsiluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);              // dS
+                        s[n][2 * hf + 1] = da[n][2 * hf + 1] * dsiluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
                     }
                 }
             }
+            uint32_t pf[4][4];
+            att_pack_p(pf, s);
+            att_mma_nn<DH>(dq, pf, sm.stream[buf][0], lane, 0, npairs);  // dQ += dS K
         }
-        uint32_t pf[4][4];
-        att_pack_p(pf, s);
-        att_mma_nn<DH>(dq, pf, sm.tile[1], lane, 0, npairs);  // dQ += dS K
+        __syncthreads();
     }
 
 #pragma unroll
@@ -342,14 +352,23 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
 }
 
 // ============================================================================================ backward: dK, dV, bias tables
-// CTA owns 64 keys; tile roles: 0 = K (own), 1 = V (own), 2 = Q (streamed), 3 = dO (streamed)
-// dynamic smem tail: s_posb[L] (padded to 16) then lane-private histograms  hist_t[4][ntime][32], hist_p[4][npos][32]
+// CTA owns 64 keys: fixed = {K, V} ; stream[buf] = {Q, dO}
+// K and V are only needed as register fragments, so they are staged through stream buffer 1 before the main loop.
+// dynamic smem tail: wcomb[npos*64+1] (padded to 16 B) then LANE-PRIVATE histograms hist_t[4][ntime][32], hist_p[4][npos][32]
+// (each lane owns one 4-byte column: plain read-modify-write, bank-conflict free, no atomics; hist_p only when the
+// position buckets are not uniform)
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int posb_bytes) {
+struct AttSmemKV {
+    static constexpr int LD = DH + 8;
+    bf16 stream[2][2][ATT_BLK * LD];
+    uint16_t ix[2][ATT_BLK * ATT_IX_LD];
+};
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int table_bytes) {
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
-    AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
-    uint8_t* s_posb = att_smem_raw + sizeof(AttSmem<DH>);
-    float* hist_t = reinterpret_cast<float*>(s_posb + posb_bytes);
+    AttSmemKV<DH>& sm = *reinterpret_cast<AttSmemKV<DH>*>(att_smem_raw);
+    float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmemKV<DH>));
+    float* hist_t = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmemKV<DH>) + table_bytes);
     const int ntime = a.bias.ntime, npos = a.bias.npos;
     float* hist_p = hist_t + 4 * ntime * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -357,23 +376,29 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
     const int L = a.L, k0 = kt * ATT_BLK;
     const long long tok0 = (long long)b * L;
     const bool has_time = a.bias.wtime != nullptr && ntime > 0;
+    const bool pos_uniform = a.bias.pos_uniform != 0;
     const int nqt = (L + ATT_BLK - 1) / ATT_BLK;
+    const unsigned sentinel = (unsigned)npos * 64u;
 
-    att_load_bias_tables<DH>(sm, a.bias, h, a.H, tid);
-    for (int i = tid; i < L; i += ATT_THREADS) s_posb[i] = a.bias.pos_bucket[i];
-    for (int i = tid; i < 4 * (ntime + npos) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
-    att_load_tile<DH>(sm.tile[0], a.k, a.ldk, tok0, k0, L, h * DH, tid);
-    att_load_tile<DH>(sm.tile[1], a.v, a.ldv, tok0, k0, L, h * DH, tid);
+    att_build_table(wcomb, a.bias, h, a.H, tid);
+    for (int i = tid; i < 4 * (ntime + (pos_uniform ? 0 : npos)) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
+    att_load_tile<DH>(sm.stream[1][0], a.k, a.ldk, tok0, k0, L, h * DH, tid);
+    att_load_tile<DH>(sm.stream[1][1], a.v, a.ldv, tok0, k0, L, h * DH, tid);
+    auto load_stream = [&](int qt, int buf) {
+        att_load_tile<DH>(sm.stream[buf][0], a.q, a.ldq, tok0, qt * ATT_BLK, L, h * DH, tid);
+        att_load_tile<DH>(sm.stream[buf][1], a.d_o, a.lddo, tok0, qt * ATT_BLK, L, h * DH, tid);
+        att_load_ix(sm.ix[buf], a.bias.bias_index, a.bias.ldix, tok0, qt * ATT_BLK, k0, L, sentinel, tid);
+    };
+    load_stream(kt, 0);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-
     uint32_t kf[DH / 16][4], vf[DH / 16][4];
-    att_load_afrag<DH>(kf, sm.tile[0], warp * 16, lane);
-    att_load_afrag<DH>(vf, sm.tile[1], warp * 16, lane);
+    att_load_afrag<DH>(kf, sm.stream[1][0], warp * 16, lane);
+    att_load_afrag<DH>(vf, sm.stream[1][1], warp * 16, lane);
+    __syncthreads();  // K/V fragments are in registers: stream buffer 1 may now be refilled
     const int j0 = k0 + warp * 16 + g, j1 = j0 + 8;
     const bool warp_live = k0 + warp * 16 < L;
-
     float dk[DH / 8][4], dv[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n)
@@ -381,59 +406,61 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
         for (int r = 0; r < 4; ++r) dk[n][r] = 0.f, dv[n][r] = 0.f;
     float* my_ht = hist_t + (warp * ntime) * 32 + lane;
     float* my_hp = hist_p + (warp * npos) * 32 + lane;
+    float pos_acc = 0.f;  // sum of dS when all cells share one position bucket
 
     for (int qt = kt; qt < nqt; ++qt) {
-        const int q0 = qt * ATT_BLK;
+        const int buf = (qt - kt) & 1;
+        if (qt + 1 < nqt) {
+            load_stream(qt + 1, buf ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        att_load_tile<DH>(sm.tile[2], a.q, a.ldq, tok0, q0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[3], a.d_o, a.lddo, tok0, q0, L, h * DH, tid);
-        att_load_mb(sm.mb, a.bias.mask_bucket, a.bias.ldmb, tok0, q0, k0, L, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        if (!warp_live) continue;
-        // query 8-blocks that can see this warp's keys (diagonal tile: queries >= first key of the warp)
-        const int nb0 = (qt == kt) ? 2 * warp : 0;          // first live 8-query block (warp-uniform)
-        const int kb0 = nb0 >> 1;                            // first live k16 block for the second GEMMs
-
-        float st[8][4], dat[8][4];
+        if (warp_live) {
+            // query 8-blocks that can see this warp's keys (diagonal tile: queries >= first key of the warp)
+            const int nb0 = (qt == kt) ? 2 * warp : 0;  // first live 8-query block (warp-uniform, even)
+            const int kb0 = nb0 >> 1;                    // first live k16 block for the second GEMMs
+            float st[8][4], dat[8][4];
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
-        att_mma_nt<DH>(st, kf, sm.tile[2], lane);   // S^T  = K Q^T   (rows = keys, cols = queries)
-        att_mma_nt<DH>(dat, vf, sm.tile[3], lane);  // dA^T = V dO^T
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (n >= nb0) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int il = n * 8 + 2 * t + (r & 1), i = q0 + il;
-                    const int jl = warp * 16 + g + ((r < 2) ? 0 : 8), j = k0 + jl;
-                    const unsigned bk = sm.mb[il * ATT_MB_LD + jl];
-                    float av = 0.f, dsv = 0.f;
-                    if (bk != ATT_MASKED) {
-                        const int pbk = s_posb[i - j];
-                        const float x = st[n][r] + sm.wpos[pbk] + sm.wtime[bk];
-                        const float sg = sigmoidf_fast(x);
-                        av = x * sg;
-                        dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));
-                        my_hp[pbk * 32] += dsv;
-                        if (has_time) my_ht[bk * 32] += dsv;
-                    }
-                    st[n][r] = av;
-                    dat[n][r] = dsv;
-                }
-            } else {
+            for (int n = 0; n < 8; ++n)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
+            att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane);   // S^T  = K Q^T   (rows = keys, cols = queries)
+            att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane);  // dA^T = V dO^T
+            const uint16_t* ix = sm.ix[buf];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (n >= nb0) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int il = n * 8 + 2 * t + (r & 1);
+                        const int jl = warp * 16 + g + ((r < 2) ? 0 : 8);
+                        const unsigned id = ix[il * ATT_IX_LD + jl];
+                        const float x = st[n][r] + wcomb[id];
+                        const float sg = sigmoidf_fast(x);
+                        const float dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));   // exactly 0 on masked cells
+                        st[n][r] = x * sg;
+                        dat[n][r] = dsv;
+                        if (id != sentinel) {
+                            if (has_time) my_ht[(id & 63u) * 32] += dsv;
+                            if (!pos_uniform) my_hp[(id >> 6) * 32] += dsv;
+                        }
+                        pos_acc += dsv;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
+                }
             }
+            uint32_t pf[4][4];
+            att_pack_p(pf, st);
+            att_mma_nn<DH>(dv, pf, sm.stream[buf][1], lane, kb0, 4);  // dV += A^T dO
+            att_pack_p(pf, dat);
+            att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, 4);  // dK += dS^T Q
         }
-        uint32_t pf[4][4];
-        att_pack_p(pf, st);
-        att_mma_nn<DH>(dv, pf, sm.tile[3], lane, kb0, 4);  // dV += A^T dO
-        att_pack_p(pf, dat);
-        att_mma_nn<DH>(dk, pf, sm.tile[2], lane, kb0, 4);  // dK += dS^T Q
+        __syncthreads();
     }
 
 #pragma unroll
@@ -462,14 +489,20 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
         }
     }
 
-    // reduce the lane-private histograms: warp w sums buckets w, w+4, ... over (4 warps x 32 lanes)
+    // bias-table gradients
+    if (pos_uniform) {
+        pos_acc = warp_sum(pos_acc);
+        if (lane == 0 && pos_acc != 0.f) atomicAdd(a.dwpos + a.bias.pos_bucket0 * a.H + h, pos_acc);
+    }
     __syncthreads();
-    for (int bk = warp; bk < npos; bk += 4) {
-        float v = 0.f;
+    if (!pos_uniform) {
+        for (int bk = warp; bk < npos; bk += 4) {
+            float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) v += hist_p[(w * npos + bk) * 32 + lane];
-        v = warp_sum(v);
-        if (lane == 0 && v != 0.f) atomicAdd(a.dwpos + bk * a.H + h, v);
+            for (int w = 0; w < 4; ++w) v += hist_p[(w * npos + bk) * 32 + lane];
+            v = warp_sum(v);
+            if (lane == 0 && v != 0.f) atomicAdd(a.dwpos + bk * a.H + h, v);
+        }
     }
     if (has_time && a.dwtime) {
         for (int bk = warp; bk < ntime; bk += 4) {

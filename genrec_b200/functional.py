@@ -33,26 +33,41 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+_ZERO_TABLES = {}
+
+
 class SeqMeta:
-    """Per-batch sequence metadata shared by all layers of one forward.  Builds the [B, L, ld] mask/bucket byte matrix
-    once (grb_hstu_mask_bucket) from the pad flags and timestamps."""
+    """Per-batch sequence metadata shared by all layers of one forward.  Builds the [B, L, ld] uint16 bias-index matrix
+    once (grb_hstu_bias_index) from the pad flags, the timestamps and the position-bucket table."""
 
     def __init__(self, pad_u8: torch.Tensor, timestamps: Optional[torch.Tensor], pos_bucket: torch.Tensor,
-                 time_thr: torch.Tensor, num_time_buckets: int = 64):
+                 time_thr: torch.Tensor, num_time_buckets: int = 64, num_pos_buckets: int = 32, pos_uniform=None):
         require_cuda(pad_u8)
         B, L = pad_u8.shape
         self.pad = pad_u8.contiguous()
         self.timestamps = timestamps.contiguous() if timestamps is not None else None
         self.pos_bucket = pos_bucket
-        self.ld = (L + 15) // 16 * 16
-        self.mask_bucket = torch.empty(B, L, self.ld, dtype=torch.uint8, device=pad_u8.device)
+        if pos_uniform is None:        # (uniform?, bucket) - a host-side property of the [L] table, cached by the caller
+            pb = pos_bucket.cpu()
+            pos_uniform = (bool((pb == pb[0]).all()), int(pb[0]))
+        self.pos_uniform, self.pos_bucket0 = pos_uniform
+        self.ld = (L + 7) // 8 * 8
+        self.bias_index = torch.empty(B, L, self.ld, dtype=torch.int16, device=pad_u8.device)
         nt = num_time_buckets if self.timestamps is not None else 0
-        check(_lib.load().grb_hstu_mask_bucket(ptr(self.timestamps), ptr(self.pad), ptr(time_thr), B, L, nt, ptr(self.mask_bucket),
-                                               self.ld, stream_ptr(pad_u8.device)))
+        if self.pos_uniform:      # collapse to one effective position bucket (see grb_hstu_seq.pos_uniform)
+            key = (L, str(pad_u8.device))
+            if key not in _ZERO_TABLES:
+                _ZERO_TABLES[key] = torch.zeros(L, dtype=torch.uint8, device=pad_u8.device)
+            pb_arg, npos_arg = _ZERO_TABLES[key], 1
+        else:
+            pb_arg, npos_arg = pos_bucket, num_pos_buckets
+        check(_lib.load().grb_hstu_bias_index(ptr(self.timestamps), ptr(self.pad), ptr(time_thr), ptr(pb_arg), B, L,
+                                              npos_arg, nt, ptr(self.bias_index), self.ld, stream_ptr(pad_u8.device)))
         _lib.count_launches(1)
 
     def struct(self) -> HstuSeq:
-        return HstuSeq(ptr(self.mask_bucket), self.ld, 1 if self.timestamps is not None else 0, ptr(self.pos_bucket))
+        return HstuSeq(ptr(self.bias_index), self.ld, 1 if self.timestamps is not None else 0, 1 if self.pos_uniform else 0,
+                       self.pos_bucket0)
 
 
 def _dims(B, L, D, H, npos, ntime, p, seed, seed_dev, layer) -> HstuDims:

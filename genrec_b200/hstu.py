@@ -80,6 +80,7 @@ class RelativePositionBias(nn.Module):
         self.num_heads = num_heads
         self.relative_attention_bias = nn.Embedding(num_buckets, num_heads)
         self._table_cache = {}
+        self._uniform_cache = {}
 
     def _relative_position_bucket(self, relative_position: torch.Tensor) -> torch.Tensor:
         nb, md = self.num_buckets, self.max_distance
@@ -100,8 +101,15 @@ class RelativePositionBias(nn.Module):
         key = (seq_len, str(device))
         if key not in self._table_cache:
             delta = torch.arange(seq_len)
-            self._table_cache[key] = self._relative_position_bucket(-delta).to(torch.uint8).to(device)
+            tbl = self._relative_position_bucket(-delta).to(torch.uint8)
+            self._uniform_cache[key] = (bool((tbl == tbl[0]).all()), int(tbl[0]))
+            self._table_cache[key] = tbl.to(device)
         return self._table_cache[key]
+
+    def uniform_of(self, seq_len: int, device):
+        """(all deltas share one bucket?, that bucket) for the table above - host-side, cached."""
+        self.bucket_of_delta(seq_len, device)
+        return self._uniform_cache[(seq_len, str(device))]
 
     def forward(self, seq_len: int, device: torch.device) -> torch.Tensor:
         """[H, L, L] dense bias - API parity only; the fused kernels never materialise it."""
@@ -195,7 +203,8 @@ class HSTULayer(nn.Module):
             ts = timestamps.contiguous() if (timestamps is not None and self.use_temporal_bias) else None
             _meta = Fn.SeqMeta(padding_mask.to(torch.uint8).contiguous(), ts,
                                self.position_bias.bucket_of_delta(L, x.device), _thresholds_on(x.device),
-                               self.temporal_bias.num_buckets if self.use_temporal_bias else 0)
+                               self.temporal_bias.num_buckets if self.use_temporal_bias else 0,
+                               self.position_bias.num_buckets, self.position_bias.uniform_of(L, x.device))
         return self._run(x, _meta, _seed, _seed_dev)
 
 
@@ -276,7 +285,9 @@ class HSTU(nn.Module):
             ts = timestamps.contiguous() if (timestamps is not None and self.use_temporal_bias) else None
             meta = Fn.SeqMeta(pad, ts, self.layers[0].position_bias.bucket_of_delta(L, input_ids.device),
                               _thresholds_on(input_ids.device),
-                              self.layers[0].temporal_bias.num_buckets if self.use_temporal_bias else 0)
+                              self.layers[0].temporal_bias.num_buckets if self.use_temporal_bias else 0,
+                              self.layers[0].position_bias.num_buckets,
+                              self.layers[0].position_bias.uniform_of(L, input_ids.device))
             for layer in self.layers:
                 layer._bf16_provider = self._bf16_provider
                 x = layer(x, None, None, timestamps, _meta=meta, _seed=seed, _seed_dev=seed_dev)

@@ -69,19 +69,25 @@ typedef struct {             /* fp32, same shapes as the parameters, accumulated
 } grb_hstu_layer_grads;
 
 typedef struct {
-    const uint8_t* mask_bucket; /* [B, L, ld_mask] from grb_hstu_mask_bucket(): temporal bucket of |ts_i - ts_j|, 255 = masked cell */
-    int ld_mask;                /* row pitch in bytes: a multiple of 16, >= L */
+    const uint16_t* bias_index; /* [B, L, ld_index] from grb_hstu_bias_index(): pos_bucket(i-j)*64 + time_bucket(|ts_i-ts_j|),
+                                   or npos*64 for a masked cell (j > i, padded key) */
+    int ld_index;               /* row pitch in ELEMENTS: a multiple of 8, >= L */
     int has_time;               /* 0: timestamps were None -> the temporal term is dropped (hstu.py:251) */
-    const uint8_t* pos_bucket;  /* [L] bucket of delta = i - j >= 0, precomputed by the host from the reference formula */
+    int pos_uniform;            /* 1 when every delta in [0, L) maps to the same position bucket (the reference's behaviour):
+                                   bias_index must then have been built with npos = 1 and an all-zero pos_bucket table */
+    int pos_bucket0;            /* that bucket (row of the [npos, H] table that is live) */
 } grb_hstu_seq;
 
 /* Per-batch integer preprocessing shared by all layers / heads / passes (replaces the index arithmetic of
- * TemporalBias._temporal_bucket, hstu.py:368-384, and the two masked_fill's, :256-259):
- *   out[b,i,j] = (j <= i && !pad[b,j]) ? clamp(trunc(log_f32(max(1,|ts_i - ts_j|)) / 0.693), 0, ntime-1) : 255
- * evaluated exactly through integer thresholds: time_thr[k] = smallest |dt| whose reference bucket is >= k (k < 64),
- * time_thr[64] = INT64_MAX.  timestamps may be NULL (bucket 0 everywhere).  pad: [B, L], 1 = input_ids == 0. */
-int grb_hstu_mask_bucket(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, int B, int L, int ntime,
-                         uint8_t* out, int ld_mask, void* stream);
+ * RelativePositionBias._relative_position_bucket (hstu.py:300-328), TemporalBias._temporal_bucket (:368-384) and the two
+ * masked_fill's (:256-259)):
+ *   tb        = clamp(trunc(log_f32(max(1,|ts_i - ts_j|)) / 0.693), 0, ntime-1)    (0 when timestamps == NULL)
+ *   out[b,i,j] = (j <= i && !pad[b,j]) ? pos_bucket[i-j] * 64 + tb : npos * 64
+ * tb is evaluated exactly through integer thresholds: time_thr[k] = smallest |dt| whose reference bucket is >= k (k < 64),
+ * time_thr[64] = INT64_MAX.  pos_bucket: [L] bucket of delta = i - j >= 0, precomputed by the host from the reference
+ * formula.  pad: [B, L], 1 = input_ids == 0. */
+int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, const uint8_t* pos_bucket, int B,
+                        int L, int npos, int ntime, uint16_t* out, int ld_index, void* stream);
 
 size_t grb_hstu_layer_saved_bytes(const grb_hstu_dims* d);
 size_t grb_hstu_layer_workspace_bytes(const grb_hstu_dims* d);
