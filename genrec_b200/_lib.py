@@ -74,6 +74,9 @@ SIGNATURES = {
     "grb_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "grb_dact": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "grb_linear_dact_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_u64, c_void_p, c_u32,
+                                         c_void_p, c_void_p]),
+    "grb_cast_rows_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_u64, c_void_p, c_u32, c_void_p]),
     "grb_layernorm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "grb_layernorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,

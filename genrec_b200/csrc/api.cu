@@ -674,6 +674,21 @@ int grb_dact(const void* g_bf16_in_out, const void* z_bf16, size_t n, int act, v
     return 0;
 }
 
+int grb_linear_dact_backward(const void* dy_bf16, const void* w_bf16, const void* z_bf16, int T, int N, int K, int act, float dropout_p,
+                             uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* g_bf16, void* stream) {
+    GRB_REQUIRE(dy_bf16 && w_bf16 && z_bf16 && g_bf16, "null argument");
+    GRB_REQUIRE(T > 0 && N % 8 == 0 && K % 8 == 0 && (act == 1 || act == 2), "bad argument");
+    GRB_CUDA(gemm_dact(act, (const bf16*)dy_bf16, (const bf16*)w_bf16, (const bf16*)z_bf16, (bf16*)g_bf16, T, K, N,
+                       make_dropout(dropout_p, seed, site, seed_dev), static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int grb_cast_rows_f32_to_bf16(const float* in, void* out_bf16, int T, int D, const float* row_scale, float dropout_p, uint64_t seed,
+                              const uint64_t* seed_dev, uint32_t site, void* stream) {
+    GRB_REQUIRE(in && out_bf16 && T > 0 && D > 0 && D % 4 == 0, "bad argument");
+    return cast_bf16(in, (bf16*)out_bf16, (size_t)T * D, D, make_dropout(dropout_p, seed, site, seed_dev), row_scale,
+                     static_cast<cudaStream_t>(stream));
+}
+
 int grb_layernorm_forward(const float* x, const float* g, const float* b, float eps, int T, int D, void* y_bf16, float* y_f32,
                           float* stats, void* stream) {
     GRB_REQUIRE(x && g && b && (y_bf16 || y_f32), "null argument");

@@ -325,6 +325,28 @@ def sasrec_attention_bwd(q, k, v, pad, out, lse, dout, H, p=0.0, seed=0, seed_de
     return dq, dk, dv
 
 
+def linear_dact_bwd(dyb, wb, z, act, p=0.0, seed=0, seed_dev=None, site=0):
+    """g[T,K] = dropmask(dyb[T,N] @ wb[N,K]) * act'(z[T,K])  (bf16)"""
+    N, K = wb.shape
+    T = dyb.numel() // N
+    g = torch.empty_like(z)
+    check(_lib.load().grb_linear_dact_backward(ptr(dyb), ptr(wb), ptr(z), T, N, K, act, float(p), int(seed), ptr(seed_dev), site, ptr(g),
+                                               stream_ptr(dyb.device)))
+    _lib.count_launches(1)
+    return g
+
+
+def cast_rows_bf16(x, row_scale=None, p=0.0, seed=0, seed_dev=None, site=0):
+    """bf16(dropmask(x) * row_scale[:, None])"""
+    D = x.shape[-1]
+    T = x.numel() // D
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().grb_cast_rows_f32_to_bf16(ptr(x), ptr(out), T, D, ptr(row_scale), float(p), int(seed), ptr(seed_dev), site,
+                                                stream_ptr(x.device)))
+    _lib.count_launches(1)
+    return out
+
+
 def dact_(g_bf16, z_bf16, act):
     check(_lib.load().grb_dact(ptr(g_bf16), ptr(z_bf16), g_bf16.numel(), act, stream_ptr(g_bf16.device)))
     _lib.count_launches(1)

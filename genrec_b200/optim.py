@@ -20,26 +20,23 @@ import torch.distributed as dist
 from . import functional as Fn
 
 
-class FlatAdam:
-    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True):
+class FlatBuffers:
+    """Device-agnostic part: one flat fp32 parameter buffer, one flat gradient buffer, one flat bf16 mirror, with every
+    ``param.data`` / ``param.grad`` re-homed as a view (256-byte aligned slots).  Works on CPU tensors too, which is how the
+    world_size-2 gloo tests exercise the data-parallel plumbing without a GPU."""
+
+    def __init__(self, model: torch.nn.Module):
         params = [p for p in model.parameters() if p.requires_grad]
         assert params, "no trainable parameters"
         dev = params[0].device
-        assert dev.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
-        self.model, self.lr, self.betas, self.eps, self.weight_decay = model, lr, betas, eps, weight_decay
-        self.group = process_group
         offs, n = [], 0
         for p in params:
             offs.append(n)
             n += (p.numel() + 63) // 64 * 64          # 256-byte aligned slots (bf16 views stay 16-byte aligned)
-        self.n = n
+        self.n, self.offsets, self.params, self.device = n, offs, params, dev
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.mirror = torch.zeros(n, dtype=torch.bfloat16, device=dev)
-        self.state = torch.zeros(4, dtype=torch.float32, device=dev)
         self._mirror_view, self._grad_view = {}, {}
         with torch.no_grad():
             for p, o in zip(params, offs):
@@ -49,14 +46,6 @@ class FlatAdam:
                 p.grad = self.grad[o:o + k].view(p.shape)
                 self._mirror_view[id(p)] = self.mirror[o:o + k].view(p.shape)
                 self._grad_view[id(p)] = p.grad
-        Fn.cast_bf16(self.flat, self.mirror)
-        self.params = params
-        # hand the mirror (and, optionally, the gradient sink) to the modules
-        for mod in model.modules():
-            if hasattr(mod, "_bf16_provider"):
-                mod._bf16_provider = self.mirror_of
-            if grad_sink and hasattr(mod, "_grad_sink"):
-                mod._grad_sink = self.grad_of
 
     def mirror_of(self, p: torch.Tensor) -> torch.Tensor:
         return self._mirror_view[id(p)]
@@ -64,16 +53,55 @@ class FlatAdam:
     def grad_of(self, p: torch.Tensor) -> Optional[torch.Tensor]:
         return self._grad_view.get(id(p))
 
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_gradients(buffers: FlatBuffers, group=None) -> float:
+    """ONE all-reduce(SUM) over the flat gradient buffer; returns the scale (1/world) the optimizer must apply, i.e. DDP's
+    gradient averaging (each rank back-propagates its own mean-over-valid-tokens loss)."""
+    w = world_size(group)
+    if w > 1:
+        dist.all_reduce(buffers.grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / w
+
+
+class FlatAdam:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True):
+        self.buffers = FlatBuffers(model)
+        dev = self.buffers.device
+        assert dev.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
+        self.model, self.lr, self.betas, self.eps, self.weight_decay = model, lr, betas, eps, weight_decay
+        self.group = process_group
+        self.n, self.flat, self.grad, self.mirror, self.params = (self.buffers.n, self.buffers.flat, self.buffers.grad,
+                                                                    self.buffers.mirror, self.buffers.params)
+        self.m = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(4, dtype=torch.float32, device=dev)
+        Fn.cast_bf16(self.flat, self.mirror)
+        # hand the mirror (and, optionally, the gradient sink) to the modules
+        for mod in model.modules():
+            if hasattr(mod, "_bf16_provider"):
+                mod._bf16_provider = self.buffers.mirror_of
+            if grad_sink and hasattr(mod, "_grad_sink"):
+                mod._grad_sink = self.buffers.grad_of
+
+    def mirror_of(self, p: torch.Tensor) -> torch.Tensor:
+        return self.buffers.mirror_of(p)
+
+    def grad_of(self, p: torch.Tensor) -> Optional[torch.Tensor]:
+        return self.buffers.grad_of(p)
+
     def world(self) -> int:
-        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        return world_size(self.group)
 
     def step(self) -> None:
         """all-reduce(SUM) -> fused Adam with grad_scale = 1/world -> mirror refresh -> grad zeroed."""
-        w = self.world()
-        if w > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        scale = allreduce_gradients(self.buffers, self.group)
         Fn.adam_step(self.flat, self.grad, self.m, self.v, self.mirror, self.state, self.lr, self.betas[0], self.betas[1],
-                     self.eps, self.weight_decay, 1.0 / w, True)
+                     self.eps, self.weight_decay, scale, True)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         pass  # the fused step already zeroed the flat gradient

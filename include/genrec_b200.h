@@ -144,6 +144,12 @@ int grb_linear_residual_forward(const void* x_bf16, const void* w_bf16, const fl
 int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_bf16, int T, int N, int K,
                         float* dx_f32, const float* dx_residual, float* dw, float* db, void* stream);
 int grb_dact(const void* g_bf16_in_out, const void* z_bf16, size_t n, int act, void* stream);
+/* g[T,K] bf16 = dropmask(dy[T,N] @ W[N,K]) * act'(z[T,K])   (backward through `act(dropout)` of a hidden layer) ; act 1 silu, 2 relu */
+int grb_linear_dact_backward(const void* dy_bf16, const void* w_bf16, const void* z_bf16, int T, int N, int K, int act,
+                             float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* g_bf16, void* stream);
+/* out_bf16[t,:] = bf16(dropmask(in[t,:]) * row_scale[t])   (row_scale may be NULL) */
+int grb_cast_rows_f32_to_bf16(const float* in, void* out_bf16, int T, int D, const float* row_scale, float dropout_p, uint64_t seed,
+                              const uint64_t* seed_dev, uint32_t site, void* stream);
 int grb_layernorm_forward(const float* x, const float* g, const float* b, float eps, int T, int D, void* y_bf16,
                           float* y_f32, float* stats, void* stream);
 int grb_layernorm_backward(const float* dy, const float* x, const float* stats, const float* g, const float* residual,

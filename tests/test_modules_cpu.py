@@ -85,3 +85,28 @@ def test_genrec_shim_import_paths():
     import genrec_b200.hstu as ours
     assert hstu.HSTU is ours.HSTU and hstu.HSTULayer is ours.HSTULayer
     assert hasattr(rq, "RqVae") and hasattr(rq, "Quantize") and hasattr(rq, "QuantizeForwardMode")
+
+
+def test_collate_mirrors_reference_known_answers(golden):
+    from genrec_b200.data import hstu_collate_fn, hstu_eval_collate_fn, sasrec_collate_fn
+    k = golden("kats.pt")
+    b = [dict(history=[1, 2, 3], timestamps=[10, 20, 30], target=4), dict(history=[5], timestamps=[7], target=6)]
+    got = hstu_collate_fn(b, 50)
+    for key in ("input_ids", "targets", "timestamps"):
+        assert torch.equal(got[key], k["hstu_collate"][key]), key
+    got = hstu_eval_collate_fn(b, 2)
+    for key in ("input_ids", "targets", "timestamps"):
+        assert torch.equal(got[key], k["hstu_eval_collate"][key]), key
+    got = sasrec_collate_fn([dict(history=[1, 2, 3], target=4), dict(history=[5], target=6)], 50)
+    for key in ("input_ids", "targets"):
+        assert torch.equal(got[key], k["sasrec_collate"][key]), key
+
+
+def test_sasrec_state_dict_schema(golden):
+    from genrec_b200.sasrec import SASRec
+    g = golden("sasrec_d64h2.pt")
+    c = g["cfg"]
+    m = SASRec(c["num_items"], c["max_seq_len"], c["embed_dim"], c["num_heads"], c["num_blocks"], c["ffn_dim"])
+    assert list(m.state_dict().keys()) == list(g["state_dict"].keys())
+    m.load_state_dict(g["state_dict"])
+    assert sum(p.numel() for p in SASRec(1000, 50, 64, 2, 2, 256).parameters()) == 159_040
