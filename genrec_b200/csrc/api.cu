@@ -267,6 +267,21 @@ int launch_row(Kern k, const Args& a, int T, cudaStream_t st) {
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
+template <int NP, class Args, class Kern>
+int launch_row_bwd(Kern k, const Args& a, int T, cudaStream_t st) {
+    int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+    int cap = sm_count() * 3;
+    k<<<need < cap ? (need < 1 ? 1 : need) : cap, ROW_THREADS, 0, st>>>(a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+#define GRB_ROW_BWD_DISPATCH(D, KERN, ARGS, T, ST)                                        \
+    do {                                                                                  \
+        if ((D) == 64) GRB_TRY((launch_row_bwd<1>(KERN<1>, ARGS, T, ST)));                \
+        else if ((D) == 128) GRB_TRY((launch_row_bwd<2>(KERN<2>, ARGS, T, ST)));          \
+        else if ((D) == 256) GRB_TRY((launch_row_bwd<4>(KERN<4>, ARGS, T, ST)));          \
+        else return fail(GRB_EINVAL, "row kernels support D in {64,128,256}, got %d", (D)); \
+    } while (0)
 #define GRB_ROW_DISPATCH(D, KERN, ARGS, T, ST)                                            \
     do {                                                                                  \
         if ((D) == 64) GRB_TRY((launch_row<1>(KERN<1>, ARGS, T, ST)));                    \
@@ -286,8 +301,9 @@ int cast_bf16(const float* in, bf16* out, size_t n, int D, const Dropout& drop, 
     return 0;
 }
 int colsum(const bf16* in, int T, int N, int ld, float* out, cudaStream_t st) {
-    int cx = (N + 63) / 64;
-    int cy = (2 * sm_count() + cx - 1) / cx;
+    if (N % 8 != 0 || ld % 8 != 0) return fail(GRB_EINVAL, "colsum needs N and ld to be multiples of 8");
+    int cx = (N + 255) / 256;
+    int cy = (4 * sm_count() + cx - 1) / cx;
     int maxy = (T + 63) / 64;
     if (cy > maxy) cy = maxy;
     if (cy < 1) cy = 1;
@@ -533,11 +549,16 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
     }
     {
-        GRB_CUDA(gemm_tn_atomic(h.logits, h.xf, dtable, C, D, T, h.ldl, D, st));  // dE[C,D] += dlogits^T xf
+        if (use_tc()) {
+            TnSpec spec{h.logits, h.xf, dtable, C, D, T, h.ldl, D, D};  // dE[C,D] += dlogits^T xf
+            GRB_CUDA(launch_tc_tn_group(&spec, 1, sm_count(), st));
+        } else {
+            GRB_CUDA(gemm_tn_atomic(h.logits, h.xf, dtable, C, D, T, h.ldl, D, st));
+        }
     }
     {
         LnBwdArgs a{h.dxf, x, h.stf, ln_g, nullptr, dx, dln_g, dln_b, T, D};
-        GRB_ROW_DISPATCH(D, ln_bwd_kernel, a, T, st);
+        GRB_ROW_BWD_DISPATCH(D, ln_bwd_kernel, a, T, st);
     }
     return 0;
 }

@@ -300,29 +300,51 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
         *reinterpret_cast<uint2*>(out + i) = o;
     }
 }
-// out[c] += sum_r in[r, c]   in: bf16 [T, ld], columns [0, N) ; grid (ceil(N/64), chunks) ; block 256 = 32 col-pairs x 8 row lanes
+// out[c] += sum_r in[r, c]   in: bf16 [T, ld] (ld % 8 == 0), columns [0, N) ; grid (ceil(N/256), chunks) ;
+// block 256 = 32 column groups of 8 (one 16-byte load each) x 8 row lanes, 4 rows in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ in, int T, int N, int ld, float* __restrict__ out) {
-    __shared__ float red[8][64];
+    __shared__ float red[8][256];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + 2 * tx;
+    const int c = blockIdx.x * 256 + 8 * tx;
     const int rows_per = (T + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(T, r0 + rows_per);
-    float s0 = 0.f, s1 = 0.f;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
     if (c < N) {
-        for (int r = r0 + ty; r < r1; r += 8) {
-            float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (size_t)r * ld + c));
-            s0 += v.x; s1 += v.y;
+        int r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(in + (size_t)(r + 8 * u) * ld + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 f = unpack_bf16(w[k]);
+                    s[2 * k] += f.x; s[2 * k + 1] += f.y;
+                }
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in + (size_t)r * ld + c);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16(w[k]);
+                s[2 * k] += f.x; s[2 * k + 1] += f.y;
+            }
         }
     }
-    red[ty][2 * tx] = s0; red[ty][2 * tx + 1] = s1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        int cc = blockIdx.x * 64 + threadIdx.x;
-        if (cc < N) atomicAdd(out + cc, s);
-    }
+    for (int k = 0; k < 8; ++k) red[ty][8 * tx + k] = s[k];
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < N) atomicAdd(out + cc, t);
 }
 
 // ------------------------------------------------------------------------------------------------ embedding

@@ -32,3 +32,16 @@ def make_batch(B, L, V, seed, pad=True, device="cpu"):
         ids[2, :] = 0; ts[2, :] = 0; tg[2, :] = 0
         tg[2, -1] = 7
     return ids.to(device), ts.to(device), tg.to(device)
+
+
+def close(a: torch.Tensor, ref: torch.Tensor, rel: float, floor: float = 1e-4) -> bool:
+    """|a - ref|_inf <= rel * max(|ref|_inf, floor)  (floor: gradients that are analytically zero, e.g. the key-projection
+    bias under a softmax, are pure rounding noise in both implementations)."""
+    a, ref = a.detach().float().cpu(), ref.detach().float().cpu()
+    return (a - ref).abs().max().item() <= rel * max(ref.abs().max().item(), floor)
+
+
+def frob_relerr(a: torch.Tensor, ref: torch.Tensor) -> float:
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    d = ref.norm().item()
+    return (a - ref).norm().item() / d if d > 0 else (a - ref).norm().item()
