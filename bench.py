@@ -107,13 +107,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cpus() -> int:
+    """Host threads this process may really use: min(affinity, cgroup CPU quota) - a 128-core host with a 16-CPU quota runs
+    32x slower when torch spawns 128 threads."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_arm(batch, L, seconds, steps=None, warmup=1):
     """The reference's CPU-eager algorithm (oracle restatement, fp32, all host threads), full train-step fwd+bwd
     (+ Adam) on a bounded sample of the same workload.  The ONLY place bench.py executes oracle/."""
     from oracle import hstu as oh
     from genrec_b200.hstu import HSTU
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     m = HSTU(**{**CFG, "max_seq_len": L, "dropout": 0.0})

@@ -14,11 +14,11 @@
 namespace grb {
 
 constexpr int CE_BSTAGES = 5;     // ring of 16 KB (128 classes x 64 k) slices of the table
-constexpr int CE_THREADS = 320;   // TMA, MMA, 8 epilogue warps
+constexpr int CE_THREADS = TC_THREADS;   // TMA, MMA, 16 epilogue warps
 
 template <int KB>
 constexpr int ce_smem_bytes() {
-    return KB * TC_TILE_BYTES + CE_BSTAGES * TC_TILE_BYTES + 2 * 32768 + 4 * 128 * 4 + 1024 + 256;
+    return KB * TC_TILE_BYTES + CE_BSTAGES * TC_TILE_BYTES + 2 * 32768 + 8 * 128 * 4 + 1024 + 256;
 }
 
 struct CeShape {
@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     unsigned char* sX = base;                                   // KB x 16 KB, resident per row block
     unsigned char* sE = sX + KB * TC_TILE_BYTES;                // ring
     unsigned char* sOut0 = sE + CE_BSTAGES * TC_TILE_BYTES;     // 2 x 32 KB staging
-    float* s_part = reinterpret_cast<float*>(sOut0 + 2 * 32768);  // [2 halves][128 rows] x {max, sum} -> 4 x 128 floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_part) + 4 * 128 * 4);
+    float* s_part = reinterpret_cast<float*>(sOut0 + 2 * 32768);  // [4 column quarters][{max, sum}][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_part) + 8 * 128 * 4);
     uint64_t* efull = bars;                      // [CE_BSTAGES]
     uint64_t* eempty = bars + CE_BSTAGES;        // [CE_BSTAGES]
     uint64_t* tfull = bars + 2 * CE_BSTAGES;     // [2]
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
         tma_prefetch_desc(&tmE);
         tma_prefetch_desc(&tmG);
         for (int s = 0; s < CE_BSTAGES; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
         mbar_init(xfull, 1);
         mbar_init(xempty, 1);
         fence_barrier_init();
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             }
         }
     } else {
-        const int sub = warp & 3, chalf = (warp - 2) >> 2;
+        const int sub = warp & 3, chalf = (warp - 2) >> 2;   // chalf: 32-column quarter 0..3 of the tile
         const int r = sub * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         const float ic = *inv_count;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+                for (int c = chalf; c < chalf + 1; ++c) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + c * 32), v);
                     const int col0 = n * 128 + c * 32;
@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             s_part[(chalf * 2 + 1) * 128 + r] = s_run;
             float* s_tl = s_part;  // re-used after the barrier below
             epi_bar_sync();
-            const float m0 = s_part[0 * 128 + r], s0 = s_part[1 * 128 + r], m1 = s_part[2 * 128 + r], s1 = s_part[3 * 128 + r];
-            const float mm = fmaxf(m0, m1);
-            const float lse = mm + __logf(s0 * __expf(m0 - mm) + s1 * __expf(m1 - mm));
+            float mm = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mm = fmaxf(mm, s_part[(q * 2 + 0) * 128 + r]);
+            float ssum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ssum += s_part[(q * 2 + 1) * 128 + r] * __expf(s_part[(q * 2 + 0) * 128 + r] - mm);
+            const float lse = mm + __logf(ssum);
             // loss: the half that saw the target column contributes -tl, half 0 contributes +lse
             float contrib = (chalf == 0 ? lse : 0.f) - tl;
             contrib = warp_sum(contrib * icr);
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 tc_fence_after();
                 unsigned char* sOut = sOut0 + acc * 32768;
 #pragma unroll 1
-                for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+                for (int c = chalf; c < chalf + 1; ++c) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + c * 32), v);
                     const int col0 = n * 128 + c * 32;

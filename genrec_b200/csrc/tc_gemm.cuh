@@ -20,7 +20,8 @@
 
 namespace grb {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 320;  // TMA, MMA, 8 epilogue warps
+constexpr int TC_EPI_WARPS = 16;   // 4 per TMEM sub-partition: each converts one 32-column chunk of the 128 x 128 tile
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA, MMA, epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB per operand per stage
 constexpr int TC_STAGE_OUT_BYTES = 64 * 1024;   // epilogue staging: 2 x bf16 [128x128] or 1 x fp32 [128x128], 128B-swizzled boxes
 constexpr int TC_SMEM_BYTES = 2 * TC_STAGES * TC_TILE_BYTES + 2 * TC_STAGE_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -66,7 +67,7 @@ GRB_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" 
 GRB_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 GRB_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 GRB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-GRB_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+GRB_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }   // the epilogue warps only
 GRB_DEVINL void tma_prefetch_desc(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[a], TC_EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     } else {
         // ===================================================================== epilogue (warps 2..9)
         const int sub = warp & 3;         // TMEM sub-partition this warp may access: lanes 32*sub .. 32*sub+31
-        const int chalf = (warp - 2) >> 2;  // which 64-column half of the tile this warp converts
+        const int cq = (warp - 2) >> 2;     // which 32-column chunk of the tile this warp converts
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int row = m0 + r;
             unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
 #pragma unroll 1
-            for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+            for (int c = cq; c < cq + 1; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = n0 + c * 32;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.nprob; ++i) { tma_prefetch_desc(&P.tmA[i]); tma_prefetch_desc(&P.tmB[i]); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid
             }
         }
     } else {
-        const int sub = warp & 3, chalf = (warp - 2) >> 2;
+        const int sub = warp & 3, cq = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < P.total_work; w += gridDim.x) {
             const TnItem it = tn_decode(P, w);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid
             tc_fence_after();
             const int row = it.m0 + sub * 32 + lane;
 #pragma unroll 1
-            for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+            for (int c = cq; c < cq + 1; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = it.n0 + c * 32;
