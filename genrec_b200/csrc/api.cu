@@ -530,12 +530,13 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     }
     ce_count_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(targets), T, h.scal, loss);
     GRB_CUDA(cudaGetLastError());
+    bool fused_dx = false;
     if (use_tc()) {
-        // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly              (hstu.py:137-146)
-        const long long* tg = reinterpret_cast<const long long*>(targets);
-        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
-        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
-        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, sm_count(), st));
+        // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly and (D <= 128) h.dxf = dlogits E
+        const long long* tg = reinterpret_cast<const long long*>(targets);                                  // (hstu.py:137-146)
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)
@@ -546,7 +547,7 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     }
     if (!want_grad) return 0;
     {
-        GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
+        if (!fused_dx) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
     }
     {
         if (use_tc()) {

@@ -1,24 +1,28 @@
-// genrec_b200 - fused tied-embedding logits + cross-entropy (forward loss AND d(loss)/d(logits)) on tcgen05.
+// genrec_b200 - fused tied-embedding logits + cross-entropy: loss, d(loss)/d(logits) AND d(loss)/d(x) on tcgen05.
 //
-// Replaces `logits = x @ E^T ; loss = cross_entropy(logits, targets, ignore_index=0)` (genrec/models/hstu.py:137-146) and
-// the autograd softmax-backward.  The [T, C] logits tensor is never written: one CTA owns a block of 128 token rows and
-// sweeps the C classes twice with the same TMA -> tcgen05.mma pipeline (the token tile stays resident in shared memory,
-// the embedding table streams from L2):
-//   sweep 0 : S = X E_n^T in TMEM  ->  per-row running (max, sum exp) + the target logit, one thread per row
-//   sweep 1 : S recomputed         ->  g = (exp(S - lse) - onehot(target)) * inv_count  ->  bf16 -> smem -> TMA store
-// so HBM sees one write of dlogits (bf16) and nothing else; the 2x K=D recompute is cheap (D <= 256).
-// dlogits then feeds the two gradient GEMMs (dX = g E, dE = g^T X) of tc_gemm.cuh.
+// Replaces `logits = x @ E^T ; loss = cross_entropy(logits, targets, ignore_index=0)` (genrec/models/hstu.py:137-146), the
+// autograd softmax-backward and the `dlogits @ E` GEMM.  The [T, C] logits tensor is never written: one CTA owns a block
+// of 128 token rows (token tile resident in shared memory) and sweeps the C classes twice with the same TMA -> tcgen05.mma
+// pipeline, the embedding table streaming from L2:
+//   sweep 0 : S = X E_n^T in TMEM  ->  per-row running (max, sum exp) + the target logit, one thread per (row, 32 columns)
+//   sweep 1 : S recomputed         ->  G = (exp(S - lse) - onehot(target)) * inv_count  ->  bf16, 128B-swizzled staging tile
+//                                      -> TMA store to dlogits (consumed by the dE = G^T X GEMM)
+//                                      -> (D <= 128) the SAME staging tile is the K-major A operand of a second MMA
+//                                         dX[128, D] += G_tile E_n, whose B operand is the E_n tile already in shared memory
+//                                         read through an MN-major descriptor; dX accumulates in TMEM over all classes.
+// HBM sees one bf16 write of dlogits (620 MB at cfg-2) and one fp32 write of dX; the K = D recompute is cheap (D <= 256).
 #pragma once
 #include "tc_gemm.cuh"
 
 namespace grb {
 
-constexpr int CE_BSTAGES = 5;     // ring of 16 KB (128 classes x 64 k) slices of the table
-constexpr int CE_THREADS = TC_THREADS;   // TMA, MMA, 16 epilogue warps
+constexpr int CE_EPI_WARPS = 16;                 // 4 per TMEM sub-partition, one 32-column quarter of the class tile each
+constexpr int CE_THREADS = 64 + 32 * CE_EPI_WARPS;   // TMA, MMA, epilogue warps
+GRB_DEVINL void ce_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CE_EPI_WARPS) : "memory"); }
 
 template <int KB>
-constexpr int ce_smem_bytes() {
-    return KB * TC_TILE_BYTES + CE_BSTAGES * TC_TILE_BYTES + 2 * 32768 + 8 * 128 * 4 + 1024 + 256;
+constexpr int ce_smem_bytes() {   // fused dX (KB <= 2) keeps the table slices of three class tiles alive: 3 * KB ring slots
+    return KB * TC_TILE_BYTES + (KB <= 2 ? 3 * KB : 5) * TC_TILE_BYTES + 2 * 32768 + 8 * 128 * 4 + 1024 + 256;
 }
 
 struct CeShape {
@@ -29,41 +33,56 @@ struct CeShape {
 template <int KB>  // k-blocks of 64: D = 64 * KB
 __global__ void __launch_bounds__(CE_THREADS, 1)
     tc_ce_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmG,
-                 CeShape sh, const long long* __restrict__ targets, const float* __restrict__ inv_count, float* __restrict__ loss) {
+                 CeShape sh, const long long* __restrict__ targets, const float* __restrict__ inv_count, float* __restrict__ loss,
+                 float* __restrict__ dx_out /* [T, 64*KB] fp32, written only when the dX fusion is compiled in (KB <= 2) */) {
+    constexpr bool FUSE_DX = KB <= 2;
+    constexpr int NS = KB <= 2 ? 3 * KB : 5;
+    constexpr int D = 64 * KB;
     extern __shared__ unsigned char ce_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ce_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sX = base;                                   // KB x 16 KB, resident per row block
-    unsigned char* sE = sX + KB * TC_TILE_BYTES;                // ring
-    unsigned char* sOut0 = sE + CE_BSTAGES * TC_TILE_BYTES;     // 2 x 32 KB staging
+    unsigned char* sE = sX + KB * TC_TILE_BYTES;                // ring of table slices [128 classes][64 d]
+    unsigned char* sOut0 = sE + NS * TC_TILE_BYTES;             // 2 x 32 KB staging (G tiles)
     float* s_part = reinterpret_cast<float*>(sOut0 + 2 * 32768);  // [4 column quarters][{max, sum}][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_part) + 8 * 128 * 4);
-    uint64_t* efull = bars;                      // [CE_BSTAGES]
-    uint64_t* eempty = bars + CE_BSTAGES;        // [CE_BSTAGES]
-    uint64_t* tfull = bars + 2 * CE_BSTAGES;     // [2]
-    uint64_t* tempty = bars + 2 * CE_BSTAGES + 2;  // [2]
-    uint64_t* xfull = bars + 2 * CE_BSTAGES + 4;   // [1]
-    uint64_t* xempty = bars + 2 * CE_BSTAGES + 5;  // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CE_BSTAGES + 6);
+    uint64_t* efull = bars;                 // [NS]   TMA -> MMA
+    uint64_t* eempty = bars + NS;           // [NS]   MMA -> TMA
+    uint64_t* tfull = bars + 2 * NS;        // [2]    S accumulator ready
+    uint64_t* tempty = bars + 2 * NS + 2;   // [2]    S accumulator drained
+    uint64_t* xfull = bars + 2 * NS + 4;    // [1]
+    uint64_t* xempty = bars + 2 * NS + 5;   // [1]
+    uint64_t* gfull = bars + 2 * NS + 6;    // [2]    G staging tile written (epilogue -> MMA)
+    uint64_t* gempty = bars + 2 * NS + 8;   // [2]    second MMA has read the staging tile
+    uint64_t* dxfull = bars + 2 * NS + 10;  // [1]    dX accumulator complete
+    uint64_t* dxempty = bars + 2 * NS + 11; // [1]    dX accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmE);
         tma_prefetch_desc(&tmG);
-        for (int s = 0; s < CE_BSTAGES; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CE_EPI_WARPS);
+            mbar_init(&gfull[a], 1); mbar_init(&gempty[a], 1);
+        }
         mbar_init(xfull, 1);
         mbar_init(xempty, 1);
+        mbar_init(dxfull, 1);
+        mbar_init(dxempty, CE_EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_dx = tmem_base + 256;
     const int tiles_per_block = 2 * sh.num_n;  // two sweeps
 
     if (warp == 0) {
+        // ===================================================================== TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, xphase = 0;
             for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
@@ -77,24 +96,49 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         mbar_wait(&eempty[stage], phase ^ 1);
                         mbar_expect_tx(&efull[stage], TC_TILE_BYTES);
                         tma_load_2d(sE + stage * TC_TILE_BYTES, &tmE, kb * 64, n0, &efull[stage]);
-                        if (++stage == CE_BSTAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // ===================================================================== MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(128, 128, 0, 0);
+            constexpr uint32_t idesc1 = umma_idesc(128, 128, 0, 0);   // S  = X   E_n^T  (both K-major)
+            constexpr uint32_t idesc2 = umma_idesc(128, 64, 0, 1);    // dX += G   E_n    (A K-major staging, B MN-major table slice)
             int stage = 0; uint32_t phase = 0, xphase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
+            // dX += G(n) E_n : reads staging buffer `buf` (two 64-class halves) and the KB ring slices that held tile n
+            auto gemm2 = [&](int first_stage, int buf, bool first) {
+                const uint32_t a_addr = smem_u32(sOut0 + buf * 32768);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    int st = first_stage + kb;
+                    if (st >= NS) st -= NS;
+                    const uint32_t b_addr = smem_u32(sE + st * TC_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {   // 128 classes = 8 k-steps of 16: staging half k/4, 32 B per step inside the row
+                        const uint64_t ad = umma_desc(a_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+                        const uint64_t bd = umma_desc(b_addr + k * 2048, 16, 1024);   // 16 class-rows of 128 B per step
+                        umma_bf16(tmem_dx + kb * 64, ad, bd, idesc2, (first && k == 0) ? 0u : 1u);
+                    }
+                    umma_commit(&eempty[st]);      // this slice of the table is no longer needed
+                }
+                umma_commit(&gempty[buf]);
+            };
             for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
                 mbar_wait(xfull, xphase);
                 xphase ^= 1;
                 tc_fence_after();
+                int prev_stage = -1, prev_buf = 0;
+                bool first_g = true;
                 for (int tile = 0; tile < tiles_per_block; ++tile) {
+                    const bool sweep1 = tile >= sh.num_n;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 128;
+                    const int tile_stage = stage;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&efull[stage], phase);
                         tc_fence_after();
@@ -102,21 +146,45 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         const uint32_t b_addr = smem_u32(sE + stage * TC_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + k * 32, 16, 1024), idesc,
+                            umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + k * 32, 16, 1024), idesc1,
                                       (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&eempty[stage]);
-                        if (++stage == CE_BSTAGES) { stage = 0; phase ^= 1; }
+                        if (!(FUSE_DX && sweep1)) umma_commit(&eempty[stage]);   // sweep 1 keeps the slice for the dX MMA
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&tfull[acc]);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (FUSE_DX && sweep1) {
+                        if (prev_stage >= 0) {   // dX MMA of the PREVIOUS class tile, once its G tile has been staged
+                            if (first_g) { mbar_wait(dxempty, dxphase ^ 1); tc_fence_after(); }
+                            mbar_wait(&gfull[prev_buf], gphase);
+                            tc_fence_after();
+                            gemm2(prev_stage, prev_buf, first_g);
+                            first_g = false;
+                            if (prev_buf == 1) gphase ^= 1;
+                        }
+                        prev_stage = tile_stage;
+                        prev_buf = gbuf;
+                        gbuf ^= 1;
+                    }
+                }
+                if (FUSE_DX) {
+                    if (first_g) { mbar_wait(dxempty, dxphase ^ 1); tc_fence_after(); }
+                    mbar_wait(&gfull[prev_buf], gphase);
+                    tc_fence_after();
+                    gemm2(prev_stage, prev_buf, first_g);
+                    if (prev_buf == 1) gphase ^= 1;
+                    umma_commit(dxfull);
+                    dxphase ^= 1;
                 }
                 umma_commit(xempty);  // every MMA that reads this row block has retired -> the producer may overwrite sX
             }
         }
     } else {
-        const int sub = warp & 3, chalf = (warp - 2) >> 2;   // chalf: 32-column quarter 0..3 of the tile
+        // ===================================================================== epilogue (16 warps)
+        const int sub = warp & 3, cq = (warp - 2) >> 2;   // TMEM sub-partition ; 32-column quarter of the class tile
         const int r = sub * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
+        int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
         const float ic = *inv_count;
         for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
             const int row = blk * 128 + r;
@@ -127,11 +195,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             for (int n = 0; n < sh.num_n; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = chalf; c < chalf + 1; ++c) {
+                {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + c * 32), v);
-                    const int col0 = n * 128 + c * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + cq * 32), v);
+                    const int col0 = n * 128 + cq * 32;
                     if (col0 + 32 > sh.C) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -159,11 +226,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // combine the two column halves of every row
-            s_part[(chalf * 2 + 0) * 128 + r] = m_run;
-            s_part[(chalf * 2 + 1) * 128 + r] = s_run;
-            float* s_tl = s_part;  // re-used after the barrier below
-            epi_bar_sync();
+            // combine the four column quarters of every row
+            s_part[(cq * 2 + 0) * 128 + r] = m_run;
+            s_part[(cq * 2 + 1) * 128 + r] = s_run;
+            ce_bar_sync();
             float mm = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) mm = fmaxf(mm, s_part[(q * 2 + 0) * 128 + r]);
@@ -171,24 +237,22 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
 #pragma unroll
             for (int q = 0; q < 4; ++q) ssum += s_part[(q * 2 + 1) * 128 + r] * __expf(s_part[(q * 2 + 0) * 128 + r] - mm);
             const float lse = mm + __logf(ssum);
-            // loss: the half that saw the target column contributes -tl, half 0 contributes +lse
-            float contrib = (chalf == 0 ? lse : 0.f) - tl;
+            // loss: quarter 0 contributes +lse, the quarter that saw the target column contributes -logit[target]
+            float contrib = (cq == 0 ? lse : 0.f) - tl;
             contrib = warp_sum(contrib * icr);
             if (lane == 0 && contrib != 0.f) atomicAdd(loss, contrib);
-            epi_bar_sync();  // everybody has read s_part before the next block overwrites it
-            (void)s_tl;
             // ------------------------------------------------------------------ sweep 1: gradient tiles
-            if (warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free (previous block's stores drained)
-            epi_bar_sync();
+            if (warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
+            ce_bar_sync();                                     // (also: everybody has read s_part)
             for (int n = 0; n < sh.num_n; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-                unsigned char* sOut = sOut0 + acc * 32768;
-#pragma unroll 1
-                for (int c = chalf; c < chalf + 1; ++c) {
+                if (FUSE_DX) mbar_wait(&gempty[gbuf], gphase ^ 1);   // the dX MMA that read this staging buffer two tiles ago is done
+                unsigned char* sOut = sOut0 + gbuf * 32768;
+                {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + c * 32), v);
-                    const int col0 = n * 128 + c * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + cq * 32), v);
+                    const int col0 = n * 128 + cq * 32;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __expf(v[i] - lse) * icr;
                     if (col0 + 32 > sh.C) {
@@ -201,29 +265,46 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         for (int i = 0; i < 32; ++i)
                             if (i == t - col0) v[i] -= icr;
                     }
-                    unsigned char* dst = sOut + (c >> 1) * 16384 + r * 128;
+                    unsigned char* dst = sOut + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 u;
                         u.x = pack_bf16(v[8 * j], v[8 * j + 1]); u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                         u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
+                        *reinterpret_cast<uint4*>(dst + ((((cq & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                fence_proxy_async();
-                epi_bar_sync();
+                fence_proxy_async();   // generic-proxy smem writes -> visible to TMA and to tcgen05.mma (async proxy)
+                ce_bar_sync();
                 if (warp == 2 && lane == 0) {
+                    if (FUSE_DX) mbar_arrive(&gfull[gbuf]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
                         if (n * 128 + h * 64 < sh.ldl) tma_store_2d(&tmG, sOut + h * 16384, n * 128 + h * 64, blk * 128);
                     tma_store_commit();
                     tma_store_wait_read1();
                 }
-                epi_bar_sync();
+                ce_bar_sync();
+                if (gbuf == 1) gphase ^= 1;
+                gbuf ^= 1;
+            }
+            if (FUSE_DX) {
+                // ------------------------------------------------------------------ dX block: TMEM -> fp32 global
+                mbar_wait(dxfull, dxphase);
+                dxphase ^= 1;
+                tc_fence_after();
+                if (cq * 32 < D) {
+                    float v[32];
+                    tmem_ld32(tmem_dx + ((uint32_t)(sub * 32) << 16) + (uint32_t)(cq * 32), v);
+                    if (row < sh.T) store_f32x32(dx_out + (size_t)row * D + cq * 32, v, 32);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dxempty);
             }
         }
         if (warp == 2 && lane == 0) tma_store_wait_read();
@@ -232,14 +313,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
-// X [T, D] bf16, E [C, D] bf16 -> G [T, ldl] bf16 (columns >= C zeroed), loss += sum_rows(lse - logit[target]) * inv_count
+// X [T, D] bf16, E [C, D] bf16 -> G [T, ldl] bf16 (columns >= C zeroed), loss += sum_rows(lse - logit[target]) * inv_count,
+// and (D <= 128) dx [T, D] fp32 = G E.  Returns through *fused_dx whether dx was produced.
 template <int KB>
 inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, int C, int ldl, const long long* targets, const float* inv_count,
-                                float* loss, int num_sms, cudaStream_t st) {
+                                float* loss, float* dx, bool* fused_dx, int num_sms, cudaStream_t st) {
     CUtensorMap tmX, tmE, tmG;
     const int D = 64 * KB;
     bool ok = make_tmap_bf16(&tmX, X, T, D, D, 64, 128) && make_tmap_bf16(&tmE, E, C, D, D, 64, 128) && make_tmap(&tmG, G, false, T, ldl, ldl, 64, 128);
@@ -248,6 +330,7 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
     sh.T = T; sh.C = C; sh.ldl = ldl;
     sh.num_m = (T + 127) / 128;
     sh.num_n = (C + 127) / 128;
+    *fused_dx = KB <= 2;
     auto kern = tc_ce_kernel<KB>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -256,7 +339,7 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
         attr_set = true;
     }
     int grid = sh.num_m < num_sms ? sh.num_m : num_sms;
-    kern<<<grid, CE_THREADS, ce_smem_bytes<KB>(), st>>>(tmX, tmE, tmG, sh, targets, inv_count, loss);
+    kern<<<grid, CE_THREADS, ce_smem_bytes<KB>(), st>>>(tmX, tmE, tmG, sh, targets, inv_count, loss, dx);
     return cudaGetLastError();
 }
 

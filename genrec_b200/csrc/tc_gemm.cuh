@@ -20,7 +20,8 @@
 
 namespace grb {
 
-constexpr int TC_EPI_WARPS = 16;   // 4 per TMEM sub-partition: each converts one 32-column chunk of the 128 x 128 tile
+constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM sub-partition: each converts 4 / (TC_EPI_WARPS / 4) 32-column chunks of the tile
+constexpr int TC_EPI_CPW = 4 / (TC_EPI_WARPS / 4);   // chunks per warp (16 warps measured slower here: register spills)
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA, MMA, epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB per operand per stage
 constexpr int TC_STAGE_OUT_BYTES = 64 * 1024;   // epilogue staging: 2 x bf16 [128x128] or 1 x fp32 [128x128], 128B-swizzled boxes
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int row = m0 + r;
             unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
 #pragma unroll 1
-            for (int c = cq; c < cq + 1; ++c) {
+            for (int c = cq * TC_EPI_CPW; c < (cq + 1) * TC_EPI_CPW; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = n0 + c * 32;

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid
             tc_fence_after();
             const int row = it.m0 + sub * 32 + lane;
 #pragma unroll 1
-            for (int c = cq; c < cq + 1; ++c) {
+            for (int c = cq * TC_EPI_CPW; c < (cq + 1) * TC_EPI_CPW; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = it.n0 + c * 32;
