@@ -254,7 +254,7 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     GRB_TRY(set_smem(hstu_attn_bwd_dq_kernel<DH>, smem_q));
     hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
     GRB_CUDA(cudaGetLastError());
-    size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos)) * 32 * sizeof(float);
+    size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos + 1)) * 32 * sizeof(float);
     GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
     hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, (int)posb);
     GRB_CUDA(cudaGetLastError());

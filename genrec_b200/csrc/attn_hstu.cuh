@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
         __syncthreads();  // tile kt (and, first time, Q + table) visible to everyone
         if (kt == 0) att_load_afrag<DH>(qf, sm.fixed[0], warp * 16, lane);
         if (warp_live) {
-            const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;  // 8-key blocks intersecting this warp's causal triangle
+            int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;  // 8-key blocks intersecting this warp's causal triangle
+            nblk = min(nblk, (L - kt * ATT_BLK + 7) >> 3);       // ... and lying below L
             const int npairs = (nblk + 1) >> 1;
             float s[8][4];
 #pragma unroll
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
             att_load_afrag<DH>(dof, sm.fixed[1], warp * 16, lane);
         }
         if (warp_live) {
-            const int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
+            int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
+            nblk = min(nblk, (L - kt * ATT_BLK + 7) >> 3);
             const int npairs = (nblk + 1) >> 1;
             float s[8][4], da[8][4];
 #pragma unroll
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
     const unsigned sentinel = (unsigned)npos * 64u;
 
     att_build_table(wcomb, a.bias, h, a.H, tid);
-    for (int i = tid; i < 4 * (ntime + (pos_uniform ? 0 : npos)) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
+    for (int i = tid; i < 4 * (ntime + (pos_uniform ? 0 : npos + 1)) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
     att_load_tile<DH>(sm.stream[1][0], a.k, a.ldk, tok0, k0, L, h * DH, tid);
     att_load_tile<DH>(sm.stream[1][1], a.v, a.ldv, tok0, k0, L, h * DH, tid);
     auto load_stream = [&](int qt, int buf) {
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
 #pragma unroll
         for (int r = 0; r < 4; ++r) dk[n][r] = 0.f, dv[n][r] = 0.f;
     float* my_ht = hist_t + (warp * ntime) * 32 + lane;
-    float* my_hp = hist_p + (warp * npos) * 32 + lane;
+    float* my_hp = hist_p + (warp * (npos + 1)) * 32 + lane;   // bin `npos` only ever receives the zeros of masked cells
     float pos_acc = 0.f;  // sum of dS when all cells share one position bucket
 
     for (int qt = kt; qt < nqt; ++qt) {
@@ -422,17 +424,19 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
             // query 8-blocks that can see this warp's keys (diagonal tile: queries >= first key of the warp)
             const int nb0 = (qt == kt) ? 2 * warp : 0;  // first live 8-query block (warp-uniform, even)
             const int kb0 = nb0 >> 1;                    // first live k16 block for the second GEMMs
+            const int nb1 = min(8, (L - qt * ATT_BLK + 7) >> 3);   // query blocks at or beyond L hold nothing (last tile of a short sequence)
+            const int kb1 = (nb1 + 1) >> 1;
             float st[8][4], dat[8][4];
 #pragma unroll
             for (int n = 0; n < 8; ++n)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
-            att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane);   // S^T  = K Q^T   (rows = keys, cols = queries)
-            att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane);  // dA^T = V dO^T
+            att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane, kb1);   // S^T  = K Q^T   (rows = keys, cols = queries)
+            att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane, kb1);  // dA^T = V dO^T
             const uint16_t* ix = sm.ix[buf];
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                if (n >= nb0) {
+                if (n >= nb0 && n < nb1) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int il = n * 8 + 2 * t + (r & 1);
@@ -443,10 +447,9 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
                         const float dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));   // exactly 0 on masked cells
                         st[n][r] = x * sg;
                         dat[n][r] = dsv;
-                        if (id != sentinel) {
-                            if (has_time) my_ht[(id & 63u) * 32] += dsv;
-                            if (!pos_uniform) my_hp[(id >> 6) * 32] += dsv;
-                        }
+                        // masked cells carry dsv == 0 exactly and index a valid (spare) bin, so no branch is needed
+                        if (has_time) my_ht[(id & 63u) * 32] += dsv;
+                        if (!pos_uniform) my_hp[(id >> 6) * 32] += dsv;
                         pos_acc += dsv;
                     }
                 } else {
@@ -456,9 +459,9 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
             }
             uint32_t pf[4][4];
             att_pack_p(pf, st);
-            att_mma_nn<DH>(dv, pf, sm.stream[buf][1], lane, kb0, 4);  // dV += A^T dO
+            att_mma_nn<DH>(dv, pf, sm.stream[buf][1], lane, kb0, kb1);  // dV += A^T dO
             att_pack_p(pf, dat);
-            att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, 4);  // dK += dS^T Q
+            att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, kb1);  // dK += dS^T Q
         }
         __syncthreads();
     }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
         for (int bk = warp; bk < npos; bk += 4) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) v += hist_p[(w * npos + bk) * 32 + lane];
+            for (int w = 0; w < 4; ++w) v += hist_p[(w * (npos + 1) + bk) * 32 + lane];
             v = warp_sum(v);
             if (lane == 0 && v != 0.f) atomicAdd(a.dwpos + bk * a.H + h, v);
         }
