@@ -494,6 +494,7 @@ int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float
 namespace {
 struct HeadWork {
     bf16* xf; float* stf; bf16* logits; float* dxf; float* scal;  // scal[0] = inv_count
+    void* ce_scratch;
     int ldl;
     size_t bytes;
 };
@@ -507,6 +508,7 @@ HeadWork carve_head(void* base, size_t T, size_t D, size_t C) {
     h.stf = (float*)take(T * 2 * 4);
     h.dxf = (float*)take(T * D * 4);
     h.scal = (float*)take(64);
+    h.ce_scratch = take(ce_scratch_bytes((int)T));
     h.logits = (bf16*)take(T * (size_t)h.ldl * 2);
     h.bytes = off;
     return h;
@@ -534,9 +536,9 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     if (use_tc()) {
         // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly and (D <= 128) h.dxf = dlogits E
         const long long* tg = reinterpret_cast<const long long*>(targets);                                  // (hstu.py:137-146)
-        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
-        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
-        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, sm_count(), st));
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)

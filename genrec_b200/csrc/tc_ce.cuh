@@ -11,6 +11,12 @@
 //                                         dX[128, D] += G_tile E_n, whose B operand is the E_n tile already in shared memory
 //                                         read through an MN-major descriptor; dX accumulates in TMEM over all classes.
 // HBM sees one bf16 write of dlogits (620 MB at cfg-2) and one fp32 write of dX; the K = D recompute is cheap (D <= 256).
+//
+// Load balance: T/128 row blocks rarely divide by the SM count (200 blocks on 148 SMs = 2 rounds at 68 % occupancy), so a
+// work item is HALF the class range of a row block: items (2b, 2b+1) always run in the same round on neighbouring CTAs
+// (the grid is persistent and even-sized), exchange their per-row (max, sum, target-logit) partials through global memory
+// with a release/acquire flag after sweep 0, and each finishes sweep 1 on its own half; dX partials meet in a pre-zeroed
+// fp32 buffer through 16-byte vector reductions.  400 half-items on 148 CTAs = 2.7 rounds of half the length.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -22,13 +28,25 @@ GRB_DEVINL void ce_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CE_EPI
 
 template <int KB>
 constexpr int ce_smem_bytes() {   // fused dX (KB <= 2) keeps the table slices of three class tiles alive: 3 * KB ring slots
-    return KB * TC_TILE_BYTES + (KB <= 2 ? 3 * KB : 5) * TC_TILE_BYTES + 2 * 32768 + 8 * 128 * 4 + 1024 + 256;
+    return KB * TC_TILE_BYTES + (KB <= 2 ? 3 * KB : 5) * TC_TILE_BYTES + 2 * 32768 + 12 * 128 * 4 + 1024 + 256;
 }
 
 struct CeShape {
     int T, C, ldl;       // tokens, classes, leading dimension of dlogits (multiple of 8, >= C)
     int num_m, num_n;
+    int n_half;          // class tiles [0, n_half) belong to half 0, [n_half, num_n) to half 1
+    float4* stats;       // [2 * num_m][128] {max, sum, target logit, -}  partials published after sweep 0
+    unsigned* flags;     // [2 * num_m] zero before launch
 };
+GRB_DEVINL void red_add_v4_ce(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+GRB_DEVINL void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+GRB_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int KB>  // k-blocks of 64: D = 64 * KB
 __global__ void __launch_bounds__(CE_THREADS, 1)
@@ -43,8 +61,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     unsigned char* sX = base;                                   // KB x 16 KB, resident per row block
     unsigned char* sE = sX + KB * TC_TILE_BYTES;                // ring of table slices [128 classes][64 d]
     unsigned char* sOut0 = sE + NS * TC_TILE_BYTES;             // 2 x 32 KB staging (G tiles)
-    float* s_part = reinterpret_cast<float*>(sOut0 + 2 * 32768);  // [4 column quarters][{max, sum}][128 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_part) + 8 * 128 * 4);
+    float* s_part = reinterpret_cast<float*>(sOut0 + 2 * 32768);  // [4 column quarters][{max, sum, target logit}][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_part) + 12 * 128 * 4);
     uint64_t* efull = bars;                 // [NS]   TMA -> MMA
     uint64_t* eempty = bars + NS;           // [NS]   MMA -> TMA
     uint64_t* tfull = bars + 2 * NS;        // [2]    S accumulator ready
@@ -79,19 +97,22 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_dx = tmem_base + 256;
-    const int tiles_per_block = 2 * sh.num_n;  // two sweeps
+    const int num_items = 2 * sh.num_m;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, xphase = 0;
-            for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
+            for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+                const int blk = w >> 1;
+                const int nb = (w & 1) ? sh.n_half : 0, ne = (w & 1) ? sh.num_n : sh.n_half;
+                const int ntile = ne - nb;
                 mbar_wait(xempty, xphase ^ 1);
                 mbar_expect_tx(xfull, KB * TC_TILE_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(sX + kb * TC_TILE_BYTES, &tmX, kb * 64, blk * 128, xfull);
                 xphase ^= 1;
-                for (int tile = 0; tile < tiles_per_block; ++tile) {
-                    const int n0 = (tile % sh.num_n) * 128;
+                for (int tile = 0; tile < 2 * ntile; ++tile) {
+                    const int n0 = (nb + tile % ntile) * 128;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&eempty[stage], phase ^ 1);
                         mbar_expect_tx(&efull[stage], TC_TILE_BYTES);
@@ -127,14 +148,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 }
                 umma_commit(&gempty[buf]);
             };
-            for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
+            for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+                const int ntile = (w & 1) ? sh.num_n - sh.n_half : sh.n_half;
                 mbar_wait(xfull, xphase);
                 xphase ^= 1;
                 tc_fence_after();
                 int prev_stage = -1, prev_buf = 0;
                 bool first_g = true;
-                for (int tile = 0; tile < tiles_per_block; ++tile) {
-                    const bool sweep1 = tile >= sh.num_n;
+                for (int tile = 0; tile < 2 * ntile; ++tile) {
+                    const bool sweep1 = tile >= ntile;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 128;
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         gbuf ^= 1;
                     }
                 }
-                if (FUSE_DX) {
+                if (FUSE_DX && ntile > 0) {
                     if (first_g) { mbar_wait(dxempty, dxphase ^ 1); tc_fence_after(); }
                     mbar_wait(&gfull[prev_buf], gphase);
                     tc_fence_after();
@@ -186,13 +208,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
         int acc = 0; uint32_t acc_phase = 0;
         int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
         const float ic = *inv_count;
-        for (int blk = blockIdx.x; blk < sh.num_m; blk += gridDim.x) {
+        for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+            const int blk = w >> 1, half = w & 1;
+            const int nb = half ? sh.n_half : 0, ne = half ? sh.num_n : sh.n_half;
             const int row = blk * 128 + r;
             const int t = row < sh.T ? (int)targets[row] : 0;
             const float icr = t != 0 ? ic : 0.f;   // ignore_index = 0 (and rows past the end)
             float m_run = -INFINITY, s_run = 0.f, tl = 0.f;
             // ------------------------------------------------------------------ sweep 0: statistics
-            for (int n = 0; n < sh.num_n; ++n) {
+            for (int n = nb; n < ne; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 {
@@ -226,25 +250,42 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // combine the four column quarters of every row
-            s_part[(cq * 2 + 0) * 128 + r] = m_run;
-            s_part[(cq * 2 + 1) * 128 + r] = s_run;
+            // combine the four column quarters of every row (this half of the classes) ...
+            s_part[(cq * 3 + 0) * 128 + r] = m_run;
+            s_part[(cq * 3 + 1) * 128 + r] = s_run;
+            s_part[(cq * 3 + 2) * 128 + r] = tl;
             ce_bar_sync();
-            float mm = -INFINITY;
+            float mh = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) mm = fmaxf(mm, s_part[(q * 2 + 0) * 128 + r]);
-            float ssum = 0.f;
+            for (int q = 0; q < 4; ++q) mh = fmaxf(mh, s_part[(q * 3 + 0) * 128 + r]);
+            float sh_ = 0.f, tlh = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ssum += s_part[(q * 2 + 1) * 128 + r] * __expf(s_part[(q * 2 + 0) * 128 + r] - mm);
+            for (int q = 0; q < 4; ++q) {
+                const float mq = s_part[(q * 3 + 0) * 128 + r];
+                sh_ += (mq == -INFINITY) ? 0.f : s_part[(q * 3 + 1) * 128 + r] * __expf(mq - mh);
+                tlh += s_part[(q * 3 + 2) * 128 + r];
+            }
+            // ... publish them, and pick up the partner item's partials for the other half of the classes
+            if (cq == 0) sh.stats[(size_t)w * 128 + r] = make_float4(mh, sh_, tlh, 0.f);
+            __threadfence();
+            ce_bar_sync();
+            if (warp == 2 && lane == 0) {
+                st_release_u32(sh.flags + w, 1u);
+                while (ld_acquire_u32(sh.flags + (w ^ 1)) == 0u) { }
+            }
+            ce_bar_sync();
+            const float4 pp = __ldcg(sh.stats + (size_t)(w ^ 1) * 128 + r);
+            const float mm = fmaxf(mh, pp.x);
+            const float ssum = ((mh == -INFINITY) ? 0.f : sh_ * __expf(mh - mm)) + ((pp.x == -INFINITY) ? 0.f : pp.y * __expf(pp.x - mm));
             const float lse = mm + __logf(ssum);
-            // loss: quarter 0 contributes +lse, the quarter that saw the target column contributes -logit[target]
-            float contrib = (cq == 0 ? lse : 0.f) - tl;
-            contrib = warp_sum(contrib * icr);
+            // loss: half 0 / quarter 0 adds lse - logit[target] once per row
+            float contrib = (half == 0 && cq == 0) ? (lse - (tlh + pp.z)) * icr : 0.f;
+            contrib = warp_sum(contrib);
             if (lane == 0 && contrib != 0.f) atomicAdd(loss, contrib);
             // ------------------------------------------------------------------ sweep 1: gradient tiles
             if (warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
             ce_bar_sync();                                     // (also: everybody has read s_part)
-            for (int n = 0; n < sh.num_n; ++n) {
+            for (int n = nb; n < ne; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 if (FUSE_DX) mbar_wait(&gempty[gbuf], gphase ^ 1);   // the dX MMA that read this staging buffer two tiles ago is done
@@ -292,15 +333,19 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 if (gbuf == 1) gphase ^= 1;
                 gbuf ^= 1;
             }
-            if (FUSE_DX) {
-                // ------------------------------------------------------------------ dX block: TMEM -> fp32 global
+            if (FUSE_DX && ne > nb) {
+                // ------------------------------------------------------------------ dX partial of this half: TMEM -> += fp32 global
                 mbar_wait(dxfull, dxphase);
                 dxphase ^= 1;
                 tc_fence_after();
                 if (cq * 32 < D) {
                     float v[32];
                     tmem_ld32(tmem_dx + ((uint32_t)(sub * 32) << 16) + (uint32_t)(cq * 32), v);
-                    if (row < sh.T) store_f32x32(dx_out + (size_t)row * D + cq * 32, v, 32);
+                    if (row < sh.T) {
+                        float* dst = dx_out + (size_t)row * D + cq * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) red_add_v4_ce(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -319,9 +364,11 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
 
 // X [T, D] bf16, E [C, D] bf16 -> G [T, ldl] bf16 (columns >= C zeroed), loss += sum_rows(lse - logit[target]) * inv_count,
 // and (D <= 128) dx [T, D] fp32 = G E.  Returns through *fused_dx whether dx was produced.
+inline size_t ce_scratch_bytes(int T) { return (size_t)2 * ((T + 127) / 128) * (128 * sizeof(float4) + sizeof(unsigned)) + 256; }
+// scratch: ce_scratch_bytes(T) bytes of device memory (partials + flags); dx must hold [T, D] fp32 and is zero-filled here
 template <int KB>
 inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, int C, int ldl, const long long* targets, const float* inv_count,
-                                float* loss, float* dx, bool* fused_dx, int num_sms, cudaStream_t st) {
+                                float* loss, float* dx, bool* fused_dx, void* scratch, int num_sms, cudaStream_t st) {
     CUtensorMap tmX, tmE, tmG;
     const int D = 64 * KB;
     bool ok = make_tmap_bf16(&tmX, X, T, D, D, 64, 128) && make_tmap_bf16(&tmE, E, C, D, D, 64, 128) && make_tmap(&tmG, G, false, T, ldl, ldl, 64, 128);
@@ -330,7 +377,16 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
     sh.T = T; sh.C = C; sh.ldl = ldl;
     sh.num_m = (T + 127) / 128;
     sh.num_n = (C + 127) / 128;
+    sh.n_half = (sh.num_n + 1) / 2;
+    sh.stats = reinterpret_cast<float4*>(scratch);
+    sh.flags = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)2 * sh.num_m * 128 * sizeof(float4));
+    cudaError_t me = cudaMemsetAsync(sh.flags, 0, (size_t)2 * sh.num_m * sizeof(unsigned), st);
+    if (me != cudaSuccess) return me;
     *fused_dx = KB <= 2;
+    if (KB <= 2) {
+        me = cudaMemsetAsync(dx, 0, (size_t)T * D * sizeof(float), st);
+        if (me != cudaSuccess) return me;
+    }
     auto kern = tc_ce_kernel<KB>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -338,7 +394,8 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int grid = sh.num_m < num_sms ? sh.num_m : num_sms;
+    // the two halves of a row block spin on each other: both must be resident at the same time -> even, persistent grid
+    int grid = 2 * sh.num_m < num_sms ? 2 * sh.num_m : (num_sms & ~1);
     kern<<<grid, CE_THREADS, ce_smem_bytes<KB>(), st>>>(tmX, tmE, tmG, sh, targets, inv_count, loss, dx);
     return cudaGetLastError();
 }
