@@ -766,14 +766,22 @@ int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, in
     if (N == 0) return 0;
     RqArgs a{x, codebooks, reinterpret_cast<long long*>(ids), emb, res, loss, res_out, (long long)N, K, levels, commitment};
     size_t smem = (size_t)K * (D + 1) * sizeof(float);
-    unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (D == 32) {
-        GRB_TRY(set_smem(rq_residual_argmin_kernel<32>, smem));
-        rq_residual_argmin_kernel<32><<<grid, RQ_THREADS, smem, st>>>(a);
+        // two rows per thread once there is more than a wave of work; one row per thread for small N (more CTAs)
+        if (N > (int64_t)sm_count() * RQ_THREADS * 2) {
+            unsigned grid = (unsigned)((N + 2 * RQ_THREADS - 1) / (2 * RQ_THREADS));
+            GRB_TRY(set_smem(rq_residual_argmin_kernel<32, 2>, smem));
+            rq_residual_argmin_kernel<32, 2><<<grid, RQ_THREADS, smem, st>>>(a);
+        } else {
+            unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
+            GRB_TRY(set_smem(rq_residual_argmin_kernel<32, 1>, smem));
+            rq_residual_argmin_kernel<32, 1><<<grid, RQ_THREADS, smem, st>>>(a);
+        }
     } else {
-        GRB_TRY(set_smem(rq_residual_argmin_kernel<64>, smem));
-        rq_residual_argmin_kernel<64><<<grid, RQ_THREADS, smem, st>>>(a);
+        unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
+        GRB_TRY(set_smem(rq_residual_argmin_kernel<64, 1>, smem));
+        rq_residual_argmin_kernel<64, 1><<<grid, RQ_THREADS, smem, st>>>(a);
     }
     GRB_CUDA(cudaGetLastError());
     return 0;

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_fwd_kernel(SasAttnArgs a
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
 
-    att_load_tile<DH>(sm.tile[0], a.q, a.ld, tok0, q0, L, h * DH, tid);
+    att_load_tile<DH>(sm.tile[0], a.q + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_fwd_kernel(SasAttnArgs a
     for (int kt = 0; kt <= qt; ++kt) {
         const int k0 = kt * ATT_BLK;
         __syncthreads();
-        att_load_tile<DH>(sm.tile[1], a.k, a.ld, tok0, k0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[2], a.v, a.ld, tok0, k0, L, h * DH, tid);
+        att_load_tile<DH>(sm.tile[1], a.k + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
+        att_load_tile<DH>(sm.tile[2], a.v + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
         cp_async_commit();
         if (tid < ATT_BLK) sm.pad_tile[tid] = (k0 + tid < L) ? a.pad[tok0 + k0 + tid] : 1;
         cp_async_wait<0>();
@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dq_kernel(SasAttnArg
     const int L = a.L, q0 = qt * ATT_BLK;
     const long long tok0 = (long long)b * L;
 
-    att_load_tile<DH>(sm.tile[0], a.q, a.ld, tok0, q0, L, h * DH, tid);
-    att_load_tile<DH>(sm.tile[3], a.d_out, a.ld, tok0, q0, L, h * DH, tid);
-    att_load_tile<DH>(sm.tile[4], a.out, a.ld, tok0, q0, L, h * DH, tid);
+    att_load_tile<DH>(sm.tile[0], a.q + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
+    att_load_tile<DH>(sm.tile[3], a.d_out + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
+    att_load_tile<DH>(sm.tile[4], a.out + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dq_kernel(SasAttnArg
     for (int kt = 0; kt <= qt; ++kt) {
         const int k0 = kt * ATT_BLK;
         __syncthreads();
-        att_load_tile<DH>(sm.tile[1], a.k, a.ld, tok0, k0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[2], a.v, a.ld, tok0, k0, L, h * DH, tid);
+        att_load_tile<DH>(sm.tile[1], a.k + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
+        att_load_tile<DH>(sm.tile[2], a.v + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
         cp_async_commit();
         if (tid < ATT_BLK) sm.pad_tile[tid] = (k0 + tid < L) ? a.pad[tok0 + k0 + tid] : 1;
         cp_async_wait<0>();
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dkdv_kernel(SasAttnA
     const long long tok0 = (long long)b * L;
     const int nqt = (L + ATT_BLK - 1) / ATT_BLK;
 
-    att_load_tile<DH>(sm.tile[0], a.k, a.ld, tok0, k0, L, h * DH, tid);
-    att_load_tile<DH>(sm.tile[1], a.v, a.ld, tok0, k0, L, h * DH, tid);
+    att_load_tile<DH>(sm.tile[0], a.k + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
+    att_load_tile<DH>(sm.tile[1], a.v + (size_t)tok0 * a.ld + h * DH, a.ld, 0, k0, L, 0, tid);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dkdv_kernel(SasAttnA
     for (int qt = kt; qt < nqt; ++qt) {
         const int q0 = qt * ATT_BLK;
         __syncthreads();
-        att_load_tile<DH>(sm.tile[2], a.q, a.ld, tok0, q0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[3], a.d_out, a.ld, tok0, q0, L, h * DH, tid);
-        att_load_tile<DH>(sm.tile[4], a.out, a.ld, tok0, q0, L, h * DH, tid);
+        att_load_tile<DH>(sm.tile[2], a.q + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
+        att_load_tile<DH>(sm.tile[3], a.d_out + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
+        att_load_tile<DH>(sm.tile[4], a.out + (size_t)tok0 * a.ld + h * DH, a.ld, 0, q0, L, 0, tid);
         cp_async_commit();
         if (tid < ATT_BLK) {
             int i = q0 + tid;

@@ -26,27 +26,35 @@ struct RqArgs {
     float commitment;
 };
 
-template <int D>
+// ROWS item rows per thread (register tile): one broadcast LDS.128 of a code word feeds 4 * ROWS FFMA, which moves the
+// inner loop from shared-memory-issue bound (ROWS = 1: 1 LDS per 4 FFMA) to FMA bound (ROWS = 2).
+template <int D, int ROWS>
 __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_kernel(RqArgs a) {
     extern __shared__ __align__(16) float rq_smem[];
     float* cb = rq_smem;             // [K][D]
     float* cn = rq_smem + a.K * D;   // [K] squared norms
     const int tid = threadIdx.x;
-    const long long row = (long long)blockIdx.x * RQ_THREADS + tid;
-    const bool live = row < a.N;
-
-    float r[D];
-    if (live) {
+    long long row[ROWS];
+    bool live[ROWS];
+    float r[ROWS][D];
 #pragma unroll
-        for (int j = 0; j < D; j += 4) {
-            float4 v = *reinterpret_cast<const float4*>(a.x + row * D + j);
-            r[j] = v.x; r[j + 1] = v.y; r[j + 2] = v.z; r[j + 3] = v.w;
+    for (int q = 0; q < ROWS; ++q) {
+        row[q] = ((long long)blockIdx.x * ROWS + q) * RQ_THREADS + tid;
+        live[q] = row[q] < a.N;
+        if (live[q]) {
+#pragma unroll
+            for (int j = 0; j < D; j += 4) {
+                float4 v = *reinterpret_cast<const float4*>(a.x + row[q] * D + j);
+                r[q][j] = v.x; r[q][j + 1] = v.y; r[q][j + 2] = v.z; r[q][j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) r[q][j] = 0.f;
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < D; ++j) r[j] = 0.f;
     }
-    float loss = 0.f;
+    float loss[ROWS];
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) loss[q] = 0.f;
 
     for (int l = 0; l < a.levels; ++l) {
         __syncthreads();
@@ -61,51 +69,69 @@ __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_kernel(RqArgs a
         }
         __syncthreads();
 
-        float xn = 0.f;
+        float xn[ROWS], best[ROWS];
+        int best_k[ROWS];
 #pragma unroll
-        for (int j = 0; j < D; ++j) xn = fmaf(r[j], r[j], xn);
-        if (a.res && live) {
+        for (int q = 0; q < ROWS; ++q) {
+            xn[q] = 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) a.res[(row * D + j) * a.levels + l] = r[j];
+            for (int j = 0; j < D; ++j) xn[q] = fmaf(r[q][j], r[q][j], xn[q]);
+            if (a.res && live[q]) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) a.res[(row[q] * D + j) * a.levels + l] = r[q][j];
+            }
+            best[q] = INFINITY;
+            best_k[q] = 0;
         }
-
-        float best = INFINITY;
-        int best_k = 0;
         for (int k = 0; k < a.K; k += 2) {
-            float d0 = 0.f, d1 = 0.f;
+            float d0[ROWS], d1[ROWS];
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) d0[q] = d1[q] = 0.f;
             const float4* c0 = reinterpret_cast<const float4*>(cb + k * D);
             const float4* c1 = reinterpret_cast<const float4*>(cb + (k + 1) * D);
 #pragma unroll
             for (int j = 0; j < D / 4; ++j) {
-                float4 u = c0[j], w = c1[j];
-                d0 = fmaf(r[4 * j], u.x, d0); d0 = fmaf(r[4 * j + 1], u.y, d0);
-                d0 = fmaf(r[4 * j + 2], u.z, d0); d0 = fmaf(r[4 * j + 3], u.w, d0);
-                d1 = fmaf(r[4 * j], w.x, d1); d1 = fmaf(r[4 * j + 1], w.y, d1);
-                d1 = fmaf(r[4 * j + 2], w.z, d1); d1 = fmaf(r[4 * j + 3], w.w, d1);
-            }
-            float dist0 = (xn + cn[k]) - 2.f * d0;
-            float dist1 = (xn + cn[k + 1]) - 2.f * d1;
-            if (dist0 < best) { best = dist0; best_k = k; }
-            if (dist1 < best) { best = dist1; best_k = k + 1; }
-        }
-        float sq = 0.f;
-        const float* cw = cb + best_k * D;
+                const float4 u = c0[j], w = c1[j];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            float e = cw[j];
-            if (a.emb && live) a.emb[(row * D + j) * a.levels + l] = e;
-            r[j] -= e;
-            sq = fmaf(r[j], r[j], sq);
+                for (int q = 0; q < ROWS; ++q) {
+                    d0[q] = fmaf(r[q][4 * j], u.x, d0[q]); d0[q] = fmaf(r[q][4 * j + 1], u.y, d0[q]);
+                    d0[q] = fmaf(r[q][4 * j + 2], u.z, d0[q]); d0[q] = fmaf(r[q][4 * j + 3], u.w, d0[q]);
+                    d1[q] = fmaf(r[q][4 * j], w.x, d1[q]); d1[q] = fmaf(r[q][4 * j + 1], w.y, d1[q]);
+                    d1[q] = fmaf(r[q][4 * j + 2], w.z, d1[q]); d1[q] = fmaf(r[q][4 * j + 3], w.w, d1[q]);
+                }
+            }
+            const float n0 = cn[k], n1 = cn[k + 1];
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) {
+                const float dist0 = (xn[q] + n0) - 2.f * d0[q];
+                const float dist1 = (xn[q] + n1) - 2.f * d1[q];
+                if (dist0 < best[q]) { best[q] = dist0; best_k[q] = k; }
+                if (dist1 < best[q]) { best[q] = dist1; best_k[q] = k + 1; }
+            }
         }
-        loss += sq + a.commitment * sq;
-        if (live) a.ids[row * a.levels + l] = best_k;
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) {
+            float sq = 0.f;
+            const float* cw = cb + best_k[q] * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float e = cw[j];
+                if (a.emb && live[q]) a.emb[(row[q] * D + j) * a.levels + l] = e;
+                r[q][j] -= e;
+                sq = fmaf(r[q][j], r[q][j], sq);
+            }
+            loss[q] += sq + a.commitment * sq;
+            if (live[q]) a.ids[row[q] * a.levels + l] = best_k[q];
+        }
     }
-    if (live) {
-        if (a.loss) a.loss[row] = loss;
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+        if (!live[q]) continue;
+        if (a.loss) a.loss[row[q]] = loss[q];
         if (a.res_out) {
 #pragma unroll
             for (int j = 0; j < D; j += 4)
-                *reinterpret_cast<float4*>(a.res_out + row * D + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                *reinterpret_cast<float4*>(a.res_out + row[q] * D + j) = make_float4(r[q][j], r[q][j + 1], r[q][j + 2], r[q][j + 3]);
         }
     }
 }
