@@ -246,18 +246,57 @@ int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
+// Fork/join helper: dQ and dK/dV are independent, both latency-bound at low occupancy -> run them concurrently (the side
+// stream and the events are created on first use, i.e. during warm-up, never while a CUDA graph is being captured).
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+};
+SideStream& side_stream() {
+    static thread_local SideStream ss;   // the backward runs on the autograd thread: one side stream per calling thread
+    return ss;
+}
+bool use_side_stream() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRB_SIDE_STREAM");   // measured: no gain at cfg-2 (both kernels already fill the SMs) -> off by default
+        v = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 template <int DH>
 int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
     size_t posb = align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);  // combined bias table
     size_t smem_q = sizeof(AttSmem<DH>) + posb;
     GRB_TRY(set_smem(hstu_attn_bwd_dq_kernel<DH>, smem_q));
-    hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
-    GRB_CUDA(cudaGetLastError());
+    SideStream& ss = side_stream();
+    const bool forked = use_side_stream() && ss.init();
+    if (forked) {
+        GRB_CUDA(cudaEventRecord(ss.fork, st));
+        GRB_CUDA(cudaStreamWaitEvent(ss.s, ss.fork, 0));
+        hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, ss.s>>>(a);
+        GRB_CUDA(cudaGetLastError());
+        GRB_CUDA(cudaEventRecord(ss.join, ss.s));
+    } else {
+        hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
+        GRB_CUDA(cudaGetLastError());
+    }
     size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos + 1)) * 32 * sizeof(float);
     GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
     hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, (int)posb);
     GRB_CUDA(cudaGetLastError());
+    if (forked) GRB_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
     return 0;
 }
 
