@@ -257,13 +257,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int tile = w / sh.splits;
             const int m0 = (tile / sh.num_n) * TC_BM, n0 = (tile % sh.num_n) * TC_BN;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
             const int r = sub * 32 + lane;  // row inside the tile == TMEM lane
             const int row = m0 + r;
+            // operands of the fused element-wise work that do not depend on the MMA (residual rows, saved pre-activations)
+            // are fetched BEFORE waiting for the accumulator, so their latency hides behind the tensor-core work
+            float pre[Epi::kPre ? TC_EPI_CPW : 1][Epi::kPre ? 32 : 1];
+            if constexpr (Epi::kPre) {
+#pragma unroll
+                for (int ci = 0; ci < TC_EPI_CPW; ++ci) {
+                    const int col0 = n0 + (cq * TC_EPI_CPW + ci) * 32;
+                    const int nvalid = min(32, sh.N - col0);
+                    if (row < sh.M && nvalid > 0) epi.preload(row, col0, nvalid, pre[ci]);
+                }
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
             unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
-#pragma unroll 1
-            for (int c = cq * TC_EPI_CPW; c < (cq + 1) * TC_EPI_CPW; ++c) {
+#pragma unroll
+            for (int ci = 0; ci < TC_EPI_CPW; ++ci) {
+                const int c = cq * TC_EPI_CPW + ci;
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32), v);
                 const int col0 = n0 + c * 32;
@@ -272,7 +284,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (row < sh.M && nvalid > 0) epi(row, col0, v, nvalid);
                 } else {
                     float w[32];
-                    if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid);
+                    if constexpr (Epi::kPre) {
+                        if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid, pre[ci]);
+                    } else {
+                        if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid);
+                    }
                     if constexpr (Epi::kOut == 3) {
                         // fp32: box c = [128 rows][32 cols] = 128 B rows, 16-byte chunk j stored at (j ^ (r & 7))
                         unsigned char* dst = sOut + c * 16384 + r * 128;
@@ -392,6 +408,7 @@ GRB_DEVINL void load_f32x32(const float* src, float (&v)[32], int nvalid) {
 template <int ACT>
 struct TcEpiBiasAct {
     static constexpr int kOut = ACT == 0 ? 1 : 2;   // tmC0 = z, tmC1 = act
+    static constexpr bool kPre = false;
     const float* bias;
     int ld;
     Dropout drop;
@@ -415,16 +432,16 @@ struct TcEpiBiasAct {
 // y = res + dropout(acc + bias) (* row_scale) -> fp32
 struct TcEpiBiasResidual {
     static constexpr int kOut = 3;
+    static constexpr bool kPre = true;
     const float* bias;
     const float* res;
     const float* row_scale;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
-        float r[32];
+    GRB_DEVINL void preload(int row, int col0, int nvalid, float (&r)[32]) const { load_f32x32(res + (size_t)row * ld + col0, r, nvalid); }
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&r)[32]) const {
         const size_t o = (size_t)row * ld + col0;
-        load_f32x32(res + o, r, nvalid);
         const float s = row_scale ? row_scale[row] : 1.f;
 #pragma unroll
         float bb[32];
@@ -437,14 +454,14 @@ struct TcEpiBiasResidual {
 template <int ACT>
 struct TcEpiDAct {
     static constexpr int kOut = 1;
+    static constexpr bool kPre = true;
     const bf16* z;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
-        float zz[32];
+    GRB_DEVINL void preload(int row, int col0, int nvalid, float (&zz)[32]) const { load_bf16x32(z + (size_t)row * ld + col0, zz, nvalid); }
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&zz)[32]) const {
         const size_t o = (size_t)row * ld + col0;
-        load_bf16x32(z + o, zz, nvalid);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             float d = ACT == 1 ? dsiluf(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
@@ -455,14 +472,16 @@ struct TcEpiDAct {
 // out = scale * acc (+ res) -> fp32
 struct TcEpiF32 {
     static constexpr int kOut = 3;
+    static constexpr bool kPre = true;
     const float* res;
     int ld;
     float scale;
     GRB_DEVINL void prepare() {}
-    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid) const {
+    GRB_DEVINL void preload(int row, int col0, int nvalid, float (&y)[32]) const {
+        if (res) load_f32x32(res + (size_t)row * ld + col0, y, nvalid);
+    }
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&y)[32]) const {
         if (res) {
-            float y[32];
-            load_f32x32(res + (size_t)row * ld + col0, y, nvalid);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = y[i] + v[i] * scale;
         } else {
@@ -474,6 +493,7 @@ struct TcEpiF32 {
 // out += scale * acc (split-K partial sums, weight gradients)
 struct TcEpiAtomicF32 {
     static constexpr int kOut = 0;
+    static constexpr bool kPre = false;
     float* out;
     int ld;
     float scale;
@@ -488,12 +508,14 @@ struct TcEpiAtomicF32 {
 // plain bf16 store
 struct TcEpiBf16 {
     static constexpr int kOut = 1;
+    static constexpr bool kPre = false;
     GRB_DEVINL void prepare() {}
     GRB_DEVINL void operator()(int, int, float (&)[32], float (&)[32], int) const {}
 };
 // plain fp32 store, arbitrary leading dimension
 struct TcEpiF32Plain {
     static constexpr int kOut = 0;
+    static constexpr bool kPre = false;
     float* out;
     int ld;
     GRB_DEVINL void prepare() {}
