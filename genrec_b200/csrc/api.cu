@@ -242,7 +242,7 @@ int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
     size_t smem = sizeof(AttSmem<DH>) + align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);
     GRB_TRY(set_smem(hstu_attn_fwd_kernel<DH>, smem));
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
-    hstu_attn_fwd_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(a);
+    launch_k(hstu_attn_fwd_kernel<DH>, grid, ATT_THREADS, smem, st, a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -285,16 +285,16 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     if (forked) {
         GRB_CUDA(cudaEventRecord(ss.fork, st));
         GRB_CUDA(cudaStreamWaitEvent(ss.s, ss.fork, 0));
-        hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, ss.s>>>(a);
+        launch_k(hstu_attn_bwd_dq_kernel<DH>, grid, ATT_THREADS, smem_q, ss.s, a);
         GRB_CUDA(cudaGetLastError());
         GRB_CUDA(cudaEventRecord(ss.join, ss.s));
     } else {
-        hstu_attn_bwd_dq_kernel<DH><<<grid, ATT_THREADS, smem_q, st>>>(a);
+        launch_k(hstu_attn_bwd_dq_kernel<DH>, grid, ATT_THREADS, smem_q, st, a);
         GRB_CUDA(cudaGetLastError());
     }
     size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos + 1)) * 32 * sizeof(float);
     GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
-    hstu_attn_bwd_dkdv_kernel<DH><<<grid, ATT_THREADS, smem_k, st>>>(a, (int)posb);
+    launch_k(hstu_attn_bwd_dkdv_kernel<DH>, grid, ATT_THREADS, smem_k, st, a, (int)posb);
     GRB_CUDA(cudaGetLastError());
     if (forked) GRB_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
     return 0;
@@ -302,7 +302,7 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
 
 template <int NP, class Args, class Kern>
 int launch_row(Kern k, const Args& a, int T, cudaStream_t st) {
-    k<<<row_grid(T), ROW_THREADS, 0, st>>>(a);
+    launch_k(k, row_grid(T), ROW_THREADS, 0, st, a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -310,7 +310,7 @@ template <int NP, class Args, class Kern>
 int launch_row_bwd(Kern k, const Args& a, int T, cudaStream_t st) {
     int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
     int cap = sm_count() * 3;
-    k<<<need < cap ? (need < 1 ? 1 : need) : cap, ROW_THREADS, 0, st>>>(a);
+    launch_k(k, need < cap ? (need < 1 ? 1 : need) : cap, ROW_THREADS, 0, st, a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -335,7 +335,7 @@ int cast_bf16(const float* in, bf16* out, size_t n, int D, const Dropout& drop, 
     size_t blocks = (n / 4 + threads - 1) / threads;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
     if (blocks < 1) blocks = 1;
-    cast_f32_bf16_kernel<<<(unsigned)blocks, threads, 0, st>>>(in, out, n, D, drop, row_scale);
+    launch_k(cast_f32_bf16_kernel, (unsigned)blocks, threads, 0, st, in, out, n, D, drop, row_scale);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -346,7 +346,7 @@ int colsum(const bf16* in, int T, int N, int ld, float* out, cudaStream_t st) {
     int maxy = (T + 63) / 64;
     if (cy > maxy) cy = maxy;
     if (cy < 1) cy = 1;
-    colsum_bf16_kernel<<<dim3(cx, cy), 256, 0, st>>>(in, T, N, ld, out);
+    launch_k(colsum_bf16_kernel, dim3(cx, cy), 256, 0, st, in, T, N, ld, out);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -501,7 +501,7 @@ int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int
     GRB_REQUIRE(ld_index >= L && ld_index % 8 == 0, "ld_index must be a multiple of 8 and >= L");
     GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS && npos >= 1 && npos <= ATT_MAX_BUCKETS, "bucket counts out of range");
     dim3 grid((ld_index + 255) / 256, L, B);
-    hstu_bias_index_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(timestamps), pad,
+    launch_k(hstu_bias_index_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(timestamps), pad,
                                                                                  reinterpret_cast<const long long*>(time_thr), pos_bucket, L,
                                                                                  ld_index, npos, ntime, out);
     GRB_CUDA(cudaGetLastError());
@@ -515,7 +515,7 @@ int grb_embed_forward(const int64_t* ids, const float* table, const float* pos_t
     GRB_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, "bad shape");
     EmbedArgs a{reinterpret_cast<const long long*>(ids), table, pos_table, x, pad, B * L, L, D, scale, mask_pad_rows,
                 make_dropout(dropout_p, seed, SITE_EMBED, seed_dev)};
-    embed_fwd_kernel<<<row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_k(embed_fwd_kernel, row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -524,7 +524,7 @@ int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float
     GRB_REQUIRE(ids && dx && dtable, "null argument");
     EmbedBwdArgs a{reinterpret_cast<const long long*>(ids), dx, dtable, dpos_table, B * L, L, D, scale, mask_pad_rows,
                    make_dropout(dropout_p, seed, SITE_EMBED, seed_dev)};
-    embed_bwd_kernel<<<row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_k(embed_bwd_kernel, row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -569,7 +569,7 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
         GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
     }
-    ce_count_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(targets), T, h.scal, loss);
+    launch_k(ce_count_kernel, 1, 1024, 0, st, reinterpret_cast<const long long*>(targets), T, h.scal, loss);
     GRB_CUDA(cudaGetLastError());
     bool fused_dx = false;
     if (use_tc()) {
@@ -581,9 +581,9 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)
-        ce_fwd_bwd_vec_kernel<8><<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
+        launch_k(ce_fwd_bwd_vec_kernel<8>, T, 256, 0, st, h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
     else
-        ce_fwd_bwd_kernel<<<T, 256, 0, st>>>(h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
+        launch_k(ce_fwd_bwd_kernel, T, 256, 0, st, h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
     GRB_CUDA(cudaGetLastError());
     }
     if (!want_grad) return 0;
@@ -644,10 +644,10 @@ int grb_sasrec_attention_forward(const grb_sasrec_dims* d, const void* q, const 
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
     if (d->D / d->H == 32) {
         GRB_TRY(set_smem(sas_attn_fwd_kernel<32>, sizeof(SasSmem<32>)));
-        sas_attn_fwd_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
+        launch_k(sas_attn_fwd_kernel<32>, grid, ATT_THREADS, sizeof(SasSmem<32>), st, a);
     } else {
         GRB_TRY(set_smem(sas_attn_fwd_kernel<64>, sizeof(SasSmem<64>)));
-        sas_attn_fwd_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
+        launch_k(sas_attn_fwd_kernel<64>, grid, ATT_THREADS, sizeof(SasSmem<64>), st, a);
     }
     GRB_CUDA(cudaGetLastError());
     return 0;
@@ -666,13 +666,13 @@ int grb_sasrec_attention_backward(const grb_sasrec_dims* d, const void* q, const
     if (d->D / d->H == 32) {
         GRB_TRY(set_smem(sas_attn_bwd_dq_kernel<32>, sizeof(SasSmem<32>)));
         GRB_TRY(set_smem(sas_attn_bwd_dkdv_kernel<32>, sizeof(SasSmem<32>)));
-        sas_attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
-        sas_attn_bwd_dkdv_kernel<32><<<grid, ATT_THREADS, sizeof(SasSmem<32>), st>>>(a);
+        launch_k(sas_attn_bwd_dq_kernel<32>, grid, ATT_THREADS, sizeof(SasSmem<32>), st, a);
+        launch_k(sas_attn_bwd_dkdv_kernel<32>, grid, ATT_THREADS, sizeof(SasSmem<32>), st, a);
     } else {
         GRB_TRY(set_smem(sas_attn_bwd_dq_kernel<64>, sizeof(SasSmem<64>)));
         GRB_TRY(set_smem(sas_attn_bwd_dkdv_kernel<64>, sizeof(SasSmem<64>)));
-        sas_attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
-        sas_attn_bwd_dkdv_kernel<64><<<grid, ATT_THREADS, sizeof(SasSmem<64>), st>>>(a);
+        launch_k(sas_attn_bwd_dq_kernel<64>, grid, ATT_THREADS, sizeof(SasSmem<64>), st, a);
+        launch_k(sas_attn_bwd_dkdv_kernel<64>, grid, ATT_THREADS, sizeof(SasSmem<64>), st, a);
     }
     GRB_CUDA(cudaGetLastError());
     return 0;
@@ -717,6 +717,7 @@ int grb_linear_backward(const void* dy_bf16, const void* w_bf16, const void* x_b
 
 namespace {
 __global__ void dact_kernel(bf16* g, const bf16* z, size_t n, int act) {
+    pdl_wait();
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     size_t stride = (size_t)gridDim.x * blockDim.x * 2;
     for (; i < n; i += stride) {
@@ -732,7 +733,7 @@ int grb_dact(const void* g_bf16_in_out, const void* z_bf16, size_t n, int act, v
     GRB_REQUIRE(g_bf16_in_out && z_bf16 && n % 2 == 0 && (act == 1 || act == 2), "bad argument");
     size_t blocks = (n / 2 + 255) / 256;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
-    dact_kernel<<<(unsigned)(blocks ? blocks : 1), 256, 0, static_cast<cudaStream_t>(stream)>>>((bf16*)const_cast<void*>(g_bf16_in_out), (const bf16*)z_bf16, n, act);
+    launch_k(dact_kernel, (unsigned)(blocks ? blocks : 1), 256, 0, static_cast<cudaStream_t>(stream), (bf16*)const_cast<void*>(g_bf16_in_out), (const bf16*)z_bf16, n, act);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -775,7 +776,7 @@ int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream
     if (n == 0) return 0;
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
-    cast_flat_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (bf16*)out_bf16, n);
+    launch_k(cast_flat_f32_bf16_kernel, (unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream), in, (bf16*)out_bf16, n);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -783,13 +784,13 @@ int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n
                   float eps, float weight_decay, float grad_scale, int zero_grad, void* stream) {
     GRB_REQUIRE(p && g && m && v && state, "null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+    launch_k(adam_tick_kernel, 1, 1, 0, st, state, beta1, beta2);
     GRB_CUDA(cudaGetLastError());
     if (n == 0) return 0;
     AdamArgs a{p, g, m, v, (bf16*)p_bf16, n, state, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grad};
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
-    adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    launch_k(adam_step_kernel, (unsigned)blocks, 256, 0, st, a);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -811,16 +812,16 @@ int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, in
         if (N > (int64_t)sm_count() * RQ_THREADS * 2) {
             unsigned grid = (unsigned)((N + 2 * RQ_THREADS - 1) / (2 * RQ_THREADS));
             GRB_TRY(set_smem(rq_residual_argmin_kernel<32, 2>, smem));
-            rq_residual_argmin_kernel<32, 2><<<grid, RQ_THREADS, smem, st>>>(a);
+            launch_k(rq_residual_argmin_kernel<32, 2>, grid, RQ_THREADS, smem, st, a);
         } else {
             unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
             GRB_TRY(set_smem(rq_residual_argmin_kernel<32, 1>, smem));
-            rq_residual_argmin_kernel<32, 1><<<grid, RQ_THREADS, smem, st>>>(a);
+            launch_k(rq_residual_argmin_kernel<32, 1>, grid, RQ_THREADS, smem, st, a);
         }
     } else {
         unsigned grid = (unsigned)((N + RQ_THREADS - 1) / RQ_THREADS);
         GRB_TRY(set_smem(rq_residual_argmin_kernel<64, 1>, smem));
-        rq_residual_argmin_kernel<64, 1><<<grid, RQ_THREADS, smem, st>>>(a);
+        launch_k(rq_residual_argmin_kernel<64, 1>, grid, RQ_THREADS, smem, st, a);
     }
     GRB_CUDA(cudaGetLastError());
     return 0;

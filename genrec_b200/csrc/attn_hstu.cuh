@@ -65,6 +65,7 @@ GRB_DEVINL int time_bucket_dev(long long dt, const long long* thr, int ntime) {
 __global__ void __launch_bounds__(256) hstu_bias_index_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad,
                                                              const long long* __restrict__ thr_g, const uint8_t* __restrict__ pos_bucket,
                                                              int L, int ld, int npos, int ntime, uint16_t* __restrict__ out) {
+    pdl_wait();
     __shared__ long long thr[ATT_MAX_BUCKETS + 1];
     for (int i = threadIdx.x; i <= ATT_MAX_BUCKETS; i += 256) thr[i] = thr_g[i];
     __syncthreads();
@@ -190,6 +191,7 @@ GRB_DEVINL void att_pack_p(uint32_t (&pf)[4][4], const float (&s)[8][4]) {
 // fixed[0] = Q ; stream[buf] = {K, V}
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs a) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
     float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH>));
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
 // fixed = {Q, dO} ; stream[buf] = {K, V}
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnArgs a) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
     float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH>));
@@ -384,6 +387,7 @@ struct AttSmemKV {
 };
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int table_bytes) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmemKV<DH>& sm = *reinterpret_cast<AttSmemKV<DH>*>(att_smem_raw);
     float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmemKV<DH>));

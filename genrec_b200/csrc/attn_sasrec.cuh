@@ -41,6 +41,7 @@ GRB_DEVINL float quad_sum(float v) {
 // tile roles: 0 = Q, 1 = K, 2 = V
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) sas_attn_fwd_kernel(SasAttnArgs a) {
+    pdl_wait();
     a.drop.resolve();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     SasSmem<DH>& sm = *reinterpret_cast<SasSmem<DH>*>(att_smem_raw);
@@ -153,6 +154,7 @@ GRB_DEVINL void sas_rowdot(float* dsum, const bf16* tdo, const bf16* to, int tid
 // backward dQ: tile roles 0 = Q, 1 = K, 2 = V, 3 = dO, 4 = O
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dq_kernel(SasAttnArgs a) {
+    pdl_wait();
     a.drop.resolve();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     SasSmem<DH>& sm = *reinterpret_cast<SasSmem<DH>*>(att_smem_raw);
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dq_kernel(SasAttnArg
 // backward dK/dV: CTA owns 64 keys ; tile roles 0 = K, 1 = V, 2 = Q, 3 = dO, 4 = O (streamed)
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dkdv_kernel(SasAttnArgs a) {
+    pdl_wait();
     a.drop.resolve();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     SasSmem<DH>& sm = *reinterpret_cast<SasSmem<DH>*>(att_smem_raw);

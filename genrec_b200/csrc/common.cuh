@@ -3,12 +3,54 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace grb {
 
 typedef __nv_bfloat16 bf16;
 
 #define GRB_DEVINL __device__ __forceinline__
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel starts with pdl_wait() (before any global access and before any early exit): when launched with the
+// programmatic-stream-serialization attribute its CTAs may be scheduled while the previous kernel on the stream drains,
+// and this instruction is where they stop until that kernel has completed and its writes are visible.  It is a no-op
+// for an ordinary launch.  Right after it the CTA releases ITS dependents: the release fires once every CTA of this grid
+// has started (and therefore passed its own wait), so the next kernel's CTAs fill SMs as this grid's last wave drains
+// and never compete with CTAs of this grid that are still to be scheduled; look-ahead is exactly one kernel.  Data
+// ordering stays the stream's own (each dependent waits for full completion of this grid) - only launch latency and
+// the per-CTA prologue (barrier init, TMEM allocation, descriptor prefetch) move off the critical path.
+GRB_DEVINL void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRB_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// launch_k(kernel, grid, block, smem, st, args...) with the PDL attribute (GRB_PDL=0 turns it off).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ----------------------------------------------------------------------------- small math
 GRB_DEVINL float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -57,6 +57,7 @@ GRB_DEVINL void gemm_load_tile(bf16* __restrict__ s, const bf16* __restrict__ g,
 template <int AMODE, int BMODE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B,
                                                                 GemmShape sh, Epi epi) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char gemm_smem[];
     epi.prepare();
     bf16* sA = reinterpret_cast<bf16*>(gemm_smem);
@@ -316,7 +317,7 @@ inline cudaError_t launch_gemm(const bf16* A, const bf16* B, int M, int N, int K
         attr_set = true;
     }
     dim3 grid((N + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(A, B, sh, epi);
+    launch_k(kern, grid, GEMM_THREADS, GEMM_SMEM_BYTES, st, A, B, sh, epi);
     return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ struct LnGateFwdArgs {
 };
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS) ln_gate_fwd_kernel(LnGateFwdArgs a) {
+    pdl_wait();
     a.drop.resolve();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * (ROW_THREADS / 32);
@@ -103,6 +104,7 @@ struct LnGateBwdArgs {
 };
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs a) {
+    pdl_wait();
     a.drop.resolve();
     __shared__ float red[4][ROW_THREADS / 32][64 * NP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -116,17 +118,28 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs 
 
     for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
         const float m1 = a.st1[2 * row], r1 = a.st1[2 * row + 1], m2 = a.st2[2 * row], r2 = a.st2[2 * row + 1];
+        // every operand of the row is requested up front (one memory round trip instead of two dependent phases)
+        float2 xv[NP], dn[NP], dyv[NP];
+        uint32_t ovp[NP], uvp[NP], zvp[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int c = 2 * lane + 64 * p;
+            xv[p] = *reinterpret_cast<const float2*>(a.x1 + (size_t)row * a.D + c);
+            dn[p] = *reinterpret_cast<const float2*>(a.dxn + (size_t)row * a.D + c);
+            dyv[p] = *reinterpret_cast<const float2*>(a.dy + (size_t)row * a.D + c);
+            ovp[p] = *reinterpret_cast<const uint32_t*>(a.O + (size_t)row * a.ldo + c);
+            uvp[p] = *reinterpret_cast<const uint32_t*>(a.U + (size_t)row * a.ldu + c);
+            zvp[p] = *reinterpret_cast<const uint32_t*>(a.zu + (size_t)row * a.ldz + c);
+        }
         float xh2[NP][2], gg[NP][2], dx1[NP][2];
         float sa = 0.f, sb = 0.f;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             int c = 2 * lane + 64 * p;
-            float2 xv = *reinterpret_cast<const float2*>(a.x1 + (size_t)row * a.D + c);
-            float2 dn = *reinterpret_cast<const float2*>(a.dxn + (size_t)row * a.D + c);
-            xh2[p][0] = (xv.x - m2) * r2; xh2[p][1] = (xv.y - m2) * r2;
-            adg2[p][0] += dn.x * xh2[p][0]; adg2[p][1] += dn.y * xh2[p][1];
-            adb2[p][0] += dn.x; adb2[p][1] += dn.y;
-            gg[p][0] = dn.x * a.g2[c]; gg[p][1] = dn.y * a.g2[c + 1];
+            xh2[p][0] = (xv[p].x - m2) * r2; xh2[p][1] = (xv[p].y - m2) * r2;
+            adg2[p][0] += dn[p].x * xh2[p][0]; adg2[p][1] += dn[p].y * xh2[p][1];
+            adb2[p][0] += dn[p].x; adb2[p][1] += dn[p].y;
+            gg[p][0] = dn[p].x * a.g2[c]; gg[p][1] = dn[p].y * a.g2[c + 1];
             sa += gg[p][0] + gg[p][1];
             sb += gg[p][0] * xh2[p][0] + gg[p][1] * xh2[p][1];
         }
@@ -134,9 +147,8 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs 
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             int c = 2 * lane + 64 * p;
-            float2 dyv = *reinterpret_cast<const float2*>(a.dy + (size_t)row * a.D + c);
-            dx1[p][0] = dyv.x + r2 * (gg[p][0] - sa - xh2[p][0] * sb);
-            dx1[p][1] = dyv.y + r2 * (gg[p][1] - sa - xh2[p][1] * sb);
+            dx1[p][0] = dyv[p].x + r2 * (gg[p][0] - sa - xh2[p][0] * sb);
+            dx1[p][1] = dyv[p].y + r2 * (gg[p][1] - sa - xh2[p][1] * sb);
             *reinterpret_cast<float2*>(a.dx1 + (size_t)row * a.D + c) = make_float2(dx1[p][0], dx1[p][1]);
         }
         // gate + LN1
@@ -145,9 +157,9 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs 
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             int c = 2 * lane + 64 * p;
-            float2 ov = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.O + (size_t)row * a.ldo + c));
-            float2 uv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.U + (size_t)row * a.ldu + c));
-            float2 zv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.zu + (size_t)row * a.ldz + c));
+            float2 ov = unpack_bf16(ovp[p]);
+            float2 uv = unpack_bf16(uvp[p]);
+            float2 zv = unpack_bf16(zvp[p]);
             float o2[2] = {ov.x, ov.y}, u2[2] = {uv.x, uv.y}, z2[2] = {zv.x, zv.y}, dzu[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -202,6 +214,7 @@ struct LnFwdArgs {
 };
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(LnFwdArgs a) {
+    pdl_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * (ROW_THREADS / 32);
     for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
@@ -232,6 +245,7 @@ struct LnBwdArgs {
 };
 template <int NP>
 __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a) {
+    pdl_wait();
     __shared__ float red[2][ROW_THREADS / 32][64 * NP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * (ROW_THREADS / 32);
@@ -288,6 +302,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(LnBwdArgs a) {
 // out_bf16[i] = bf16(dropmask(in[i]) * row_scale[row])       (n = T*D elements, D = row length)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n, int D, Dropout drop,
                                      const float* __restrict__ row_scale) {
+    pdl_wait();
     drop.resolve();
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -303,6 +318,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
 // out[c] += sum_r in[r, c]   in: bf16 [T, ld] (ld % 8 == 0), columns [0, N) ; grid (ceil(N/256), chunks) ;
 // block 256 = 32 column groups of 8 (one 16-byte load each) x 8 row lanes, 4 rows in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ in, int T, int N, int ld, float* __restrict__ out) {
+    pdl_wait();
     __shared__ float red[8][256];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 256 + 8 * tx;
@@ -356,6 +372,7 @@ struct EmbedArgs {
     Dropout drop;
 };
 __global__ void __launch_bounds__(ROW_THREADS) embed_fwd_kernel(EmbedArgs a) {
+    pdl_wait();
     a.drop.resolve();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * (ROW_THREADS / 32);
@@ -386,6 +403,7 @@ struct EmbedBwdArgs {
     Dropout drop;
 };
 __global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) {
+    pdl_wait();
     a.drop.resolve();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * (ROW_THREADS / 32);
@@ -404,6 +422,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) 
 // ------------------------------------------------------------------------------------------------ cross entropy on bf16 logits
 // count = #(targets != 0)  -> inv_count (0 if none)
 __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* __restrict__ inv_count, float* __restrict__ loss) {
+    pdl_wait();
     __shared__ int red[32];
     int c = 0;
     for (int i = threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;
@@ -422,6 +441,7 @@ __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* 
 __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ tg,
                                                         const float* __restrict__ inv_count, float* __restrict__ loss,
                                                         int write_grad) {
+    pdl_wait();
     __shared__ float red[8];
     __shared__ float bc[2];
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -478,6 +498,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(bf16* __restrict__ logi
 template <int NCH>
 __global__ void __launch_bounds__(256) ce_fwd_bwd_vec_kernel(bf16* __restrict__ logits, int ld, int C, const long long* __restrict__ tg,
                                                             const float* __restrict__ inv_count, float* __restrict__ loss, int write_grad) {
+    pdl_wait();
     __shared__ float red[8];
     __shared__ float bc[3];
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -579,6 +600,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_vec_kernel(bf16* __restrict__ 
 // ------------------------------------------------------------------------------------------------ fused Adam (torch.optim.Adam semantics)
 // state[0] = step (as float), state[1] = 1 - beta1^step, state[2] = 1 - beta2^step ; ticked on device so a CUDA graph replays correctly
 __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
+    pdl_wait();
     float step = state[0] + 1.f;
     state[0] = step;
     state[1] = 1.f - powf(beta1, step);
@@ -592,6 +614,7 @@ struct AdamArgs {
     int zero_grad;
 };
 __global__ void adam_step_kernel(AdamArgs a) {
+    pdl_wait();
     const float bc1 = a.state[1], bc2 = a.state[2];
     const float step_size = a.lr / bc1;
     const float inv_sqrt_bc2 = rsqrtf(bc2);
@@ -612,6 +635,7 @@ __global__ void adam_step_kernel(AdamArgs a) {
     }
 }
 __global__ void cast_flat_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+    pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);

@@ -30,6 +30,7 @@ struct RqArgs {
 // inner loop from shared-memory-issue bound (ROWS = 1: 1 LDS per 4 FFMA) to FMA bound (ROWS = 2).
 template <int D, int ROWS>
 __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_kernel(RqArgs a) {
+    pdl_wait();
     extern __shared__ __align__(16) float rq_smem[];
     float* cb = rq_smem;             // [K][D]
     float* cn = rq_smem + a.K * D;   // [K] squared norms

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail
     const uint32_t tmem_dx = tmem_base + 256;
     const int num_items = 2 * sh.num_m;
 
@@ -396,7 +397,7 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
     }
     // the two halves of a row block spin on each other: both must be resident at the same time -> even, persistent grid
     int grid = 2 * sh.num_m < num_sms ? 2 * sh.num_m : (num_sms & ~1);
-    kern<<<grid, CE_THREADS, ce_smem_bytes<KB>(), st>>>(tmX, tmE, tmG, sh, targets, inv_count, loss, dx);
+    launch_k(kern, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, loss, dx);
     return cudaGetLastError();
 }
 

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail
 
     const int num_work = sh.num_m * sh.num_n * sh.splits;
 
@@ -595,7 +596,7 @@ inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, in
     }
     int work = sh.num_m * sh.num_n * sh.splits;
     int grid = work < num_sms ? work : num_sms;
-    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmB, tmC0, tmC1, sh, epi);
+    launch_k(kern, grid, TC_THREADS, TC_SMEM_BYTES, st, tmA, tmB, tmC0, tmC1, sh, epi);
     return cudaGetLastError();
 }
 

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -206,7 +207,7 @@ inline cudaError_t launch_tc_tn_group(const TnSpec* specs, int n, int num_sms, c
         attr_set = true;
     }
     int grid = work < num_sms ? work : num_sms;
-    tc_tn_group_kernel<<<grid, TC_THREADS, TN_SMEM_BYTES, st>>>(P);
+    launch_k(tc_tn_group_kernel, grid, TC_THREADS, TN_SMEM_BYTES, st, P);
     return cudaGetLastError();
 }
 
