@@ -330,7 +330,7 @@ int launch_row_bwd(Kern k, const Args& a, int T, cudaStream_t st) {
     } while (0)
 
 int cast_bf16(const float* in, bf16* out, size_t n, int D, const Dropout& drop, const float* row_scale, cudaStream_t st) {
-    GRB_REQUIRE(n % 4 == 0, "cast length must be a multiple of 4");
+    GRB_REQUIRE(D > 0 && D % 4 == 0 && n % (size_t)D == 0, "cast needs rows of a multiple-of-4 length D");
     int threads = 256;
     size_t blocks = (n / 4 + threads - 1) / threads;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;

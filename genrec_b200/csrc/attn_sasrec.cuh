@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_fwd_kernel(SasAttnArgs a
                 if (a.drop.thresh) {
                     const int jl = n * 8 + 2 * t + (r & 1);
                     const int i = (r < 2) ? i0 : i1;
-                    p = a.drop.apply(p, (((size_t)b * a.H + h) * L + i) * L + (k0 + jl));
+                    p = a.drop.apply(p, (uint32_t)((b * a.H + h) * L + i), (uint32_t)(k0 + jl));
                 }
                 s[n][r] = p;
             }
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dq_kernel(SasAttnArg
                 float dsv = 0.f;
                 if (valid) {
                     float p = __expf(s[n][r] * a.scale - ((r < 2) ? lse0 : lse1));
-                    float dA = a.drop.apply(da[n][r], (((size_t)b * a.H + h) * L + i) * L + j);
+                    float dA = a.drop.apply(da[n][r], (uint32_t)((b * a.H + h) * L + i), (uint32_t)j);
                     dsv = p * (dA - ((r < 2) ? ds0 : ds1)) * a.scale;
                 }
                 s[n][r] = dsv;
@@ -291,9 +291,9 @@ __global__ void __launch_bounds__(ATT_THREADS) sas_attn_bwd_dkdv_kernel(SasAttnA
                 float pd = 0.f, dsv = 0.f;
                 if (valid) {
                     float p = __expf(st[n][r] * a.scale - sm.lse_tile[il]);
-                    size_t idx = (((size_t)b * a.H + h) * L + i) * L + j;
-                    pd = a.drop.apply(p, idx);
-                    float dA = a.drop.apply(dat[n][r], idx);
+                    const uint32_t drow = (uint32_t)((b * a.H + h) * L + i);
+                    pd = a.drop.apply(p, drow, (uint32_t)j);
+                    float dA = a.drop.apply(dat[n][r], drow, (uint32_t)j);
                     dsv = p * (dA - sm.dsum_tile[il]) * a.scale;
                 }
                 st[n][r] = pd;

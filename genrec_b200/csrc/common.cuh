@@ -53,7 +53,18 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 // ----------------------------------------------------------------------------- small math
-GRB_DEVINL float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+GRB_DEVINL float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+GRB_DEVINL float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+GRB_DEVINL float sigmoidf_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
 GRB_DEVINL float siluf(float x) { return x * sigmoidf_fast(x); }
 // d/dx silu(x) = s * (1 + x * (1 - s))
 GRB_DEVINL float dsiluf(float x) {
@@ -83,48 +94,68 @@ GRB_DEVINL float warp_max(float v) {
 }
 
 // ----------------------------------------------------------------------------- dropout RNG
-// Counter-based: keep(seed, site, idx) is a pure function, so the backward pass re-derives the forward mask
-// instead of storing it.  One 64-bit mix (splitmix64 finaliser) per element -> 32 uniform bits.
-GRB_DEVINL uint32_t rng_u32(uint64_t seed, uint32_t site, uint64_t idx) {
-    // 32-bit mixing (two rounds of a murmur3-style finaliser keyed by seed halves and the site): ~12 integer ops,
-    // no 64-bit multiplies.  idx < 2^40 in practice; its high bits are folded in.
-    uint32_t k0 = (uint32_t)seed ^ (site * 0x9E3779B1u), k1 = (uint32_t)(seed >> 32) + 0x7F4A7C15u;
-    uint32_t x = (uint32_t)idx ^ k0;
-    x += (uint32_t)(idx >> 32) * 0x85EBCA6Bu;
-    x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x += k1; x *= 0x846CA68Bu;
-    x ^= x >> 16; x *= 0x9E3779B1u;
-    x ^= x >> 15;
-    return x;
-}
+// Counter-based: keep(seed, site, row, col) is a pure function, so the backward pass re-derives the forward mask
+// instead of storing it.  Elements are addressed by (row, column) of the [rows, cols] operand the mask belongs to -
+// 32-bit arithmetic only.  A row contributes two mixed keys (computed once per row and thread); one two-round
+// multiply / xor-shift mix per column PAIR then serves two neighbouring columns: column c takes the low (c even) or
+// high (c odd) 16 bits of the pair's hash and is dropped when they are below a 16-bit threshold (p is honoured to
+// 2^-16 and the keep scale is the exact reciprocal of the realised keep probability, so the expectation is
+// unchanged).  tests/test_linear_gpu.py restates the function in numpy and checks masks bit for bit, plus the
+// row/column cross-correlations against those of an ideal generator.
+struct DropRowKeys {
+    uint32_t ka, kb;
+};
 struct Dropout {
     uint64_t seed;
     const unsigned long long* seed_dev;  // nullable: *seed_dev is added to seed at kernel start (CUDA-graph-safe reseeding)
-    uint32_t thresh;  // drop when rng < thresh ; thresh = p * 2^32
-    float scale;      // 1 / (1 - p) ; p == 0 -> thresh = 0, scale = 1
+    uint32_t thresh;  // drop when the element's 16 random bits < thresh ; thresh = round(p * 2^16)
+    float scale;      // 2^16 / (2^16 - thresh) ; p == 0 -> thresh = 0, scale = 1
     uint32_t site;
     GRB_DEVINL void resolve() {
         if (thresh != 0u && seed_dev) seed += *seed_dev;
         seed_dev = nullptr;
     }
-    GRB_DEVINL float apply(float v, uint64_t idx) const {
-        if (thresh == 0u) return v;
-        return rng_u32(seed, site, idx) < thresh ? 0.f : v * scale;
+    GRB_DEVINL DropRowKeys row_keys(uint32_t row) const {
+        const uint32_t k0 = (uint32_t)seed ^ (site * 0x9E3779B1u), k1 = (uint32_t)(seed >> 32) + 0x7F4A7C15u;
+        DropRowKeys r;
+        r.ka = (row ^ k1) * 0x9E3779B1u;
+        r.ka ^= r.ka >> 16;
+        uint32_t b = r.ka * 0x846CA68Bu;
+        b ^= b >> 15;
+        r.kb = k0 ^ b;
+        return r;
     }
+    static GRB_DEVINL uint32_t pair_hash(const DropRowKeys& r, uint32_t colpair) {
+        uint32_t x = (colpair ^ r.kb) * 0x7FEB352Du;
+        x ^= x >> 15;
+        x ^= r.ka;
+        x *= 0x846CA68Bu;
+        x ^= x >> 16;
+        return x;
+    }
+    GRB_DEVINL float apply(float v, uint32_t row, uint32_t col) const {
+        if (thresh == 0u) return v;
+        const uint32_t h = pair_hash(row_keys(row), col >> 1);
+        const uint32_t u = (col & 1u) ? (h >> 16) : (h & 0xffffu);
+        return u < thresh ? 0.f : v * scale;
+    }
+    // two neighbouring columns 2 * colpair, 2 * colpair + 1 with one hash
+    GRB_DEVINL void apply2p(float& v0, float& v1, uint32_t row, uint32_t colpair) const {
+        if (thresh == 0u) return;
+        const uint32_t h = pair_hash(row_keys(row), colpair);
+        v0 = (h & 0xffffu) < thresh ? 0.f : v0 * scale;
+        v1 = (h >> 16) < thresh ? 0.f : v1 * scale;
+    }
+    GRB_DEVINL void apply2(float& v0, float& v1, uint32_t row, uint32_t col_even) const { apply2p(v0, v1, row, col_even >> 1); }
 };
 inline Dropout make_dropout(float p, uint64_t seed, uint32_t site, const void* seed_dev = nullptr) {
     Dropout d;
     d.seed = seed;
     d.seed_dev = static_cast<const unsigned long long*>(seed_dev);
     d.site = site;
-    if (p <= 0.f) {
-        d.thresh = 0u;
-        d.scale = 1.f;
-    } else {
-        double t = (double)p * 4294967296.0;
-        d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
-        d.scale = 1.f / (1.f - p);
-    }
+    double t = (double)p * 65536.0 + 0.5;
+    d.thresh = p <= 0.f ? 0u : (t >= 65536.0 ? 65536u : (uint32_t)t);
+    d.scale = d.thresh >= 65536u ? 0.f : 65536.f / (float)(65536u - d.thresh);
     return d;
 }
 

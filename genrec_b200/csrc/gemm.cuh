@@ -171,7 +171,8 @@ struct EpiBiasSilu {
         uint32_t zz = pack_bf16(v0, v1);
         *reinterpret_cast<uint32_t*>(z_out + o) = zz;
         float2 zr = unpack_bf16(zz);  // activation of the ROUNDED pre-activation (what the backward recomputes from)
-        float a0 = drop.apply(siluf(zr.x), o), a1 = drop.apply(siluf(zr.y), o + 1);
+        float a0 = siluf(zr.x), a1 = siluf(zr.y);
+        drop.apply2(a0, a1, row, col);
         *reinterpret_cast<uint32_t*>(act_out + o) = pack_bf16(a0, a1);
     }
 };
@@ -201,8 +202,9 @@ struct EpiBiasRelu {
         uint32_t zz = pack_bf16(v0, v1);
         *reinterpret_cast<uint32_t*>(z_out + o) = zz;
         float2 zr = unpack_bf16(zz);
-        *reinterpret_cast<uint32_t*>(act_out + o) =
-            pack_bf16(drop.apply(fmaxf(zr.x, 0.f), o), drop.apply(fmaxf(zr.y, 0.f), o + 1));
+        float a0 = fmaxf(zr.x, 0.f), a1 = fmaxf(zr.y, 0.f);
+        drop.apply2(a0, a1, row, col);
+        *reinterpret_cast<uint32_t*>(act_out + o) = pack_bf16(a0, a1);
     }
 };
 // y = res + dropout(acc + bias) ; fp32 out (+ optional row mask multiply for SASRec)
@@ -217,7 +219,10 @@ struct EpiBiasResidual {
     GRB_DEVINL void operator()(int row, int col, float v0, float v1) const {
         size_t o = (size_t)row * ld + col;
         float2 r = *reinterpret_cast<const float2*>(res + o);
-        float y0 = r.x + drop.apply(v0 + bias[col], o), y1 = r.y + drop.apply(v1 + bias[col + 1], o + 1);
+        float y0 = v0 + bias[col], y1 = v1 + bias[col + 1];
+        drop.apply2(y0, y1, row, col);
+        y0 += r.x;
+        y1 += r.y;
         if (row_scale) {
             float s = row_scale[row];
             y0 *= s;
@@ -237,8 +242,7 @@ struct EpiDAct {
     GRB_DEVINL void operator()(int row, int col, float v0, float v1) const {
         size_t o = (size_t)row * ld + col;
         float2 zz = unpack_bf16(*reinterpret_cast<const uint32_t*>(z + o));
-        v0 = drop.apply(v0, o);
-        v1 = drop.apply(v1, o + 1);
+        drop.apply2(v0, v1, row, col);
         float d0 = ACT == 0 ? dsiluf(zz.x) : (zz.x > 0.f ? 1.f : 0.f);
         float d1 = ACT == 0 ? dsiluf(zz.y) : (zz.y > 0.f ? 1.f : 0.f);
         *reinterpret_cast<uint32_t*>(out + o) = pack_bf16(v0 * d0, v1 * d1);

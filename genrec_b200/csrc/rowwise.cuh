@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_gate_fwd_kernel(LnGateFwdArgs 
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             int c = 2 * lane + 64 * p;
+            float gv[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float n = (o[p][e] - s1.mean) * s1.rstd * a.g1[c + e] + a.b1[c + e];
-                xv[p][e] += a.drop.apply(n * u[p][e], (size_t)row * a.D + c + e);
-            }
+            for (int e = 0; e < 2; ++e) gv[e] = ((o[p][e] - s1.mean) * s1.rstd * a.g1[c + e] + a.b1[c + e]) * u[p][e];
+            a.drop.apply2(gv[0], gv[1], row, c);
+            xv[p][0] += gv[0];
+            xv[p][1] += gv[1];
             *reinterpret_cast<float2*>(a.x1 + (size_t)row * a.D + c) = make_float2(xv[p][0], xv[p][1]);
         }
         LnStats s2 = row_stats<NP>(xv, a.D, a.eps);
@@ -161,9 +162,11 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_gate_bwd_kernel(LnGateBwdArgs 
             float2 uv = unpack_bf16(uvp[p]);
             float2 zv = unpack_bf16(zvp[p]);
             float o2[2] = {ov.x, ov.y}, u2[2] = {uv.x, uv.y}, z2[2] = {zv.x, zv.y}, dzu[2];
+            float dGv[2] = {dx1[p][0], dx1[p][1]};
+            a.drop.apply2(dGv[0], dGv[1], row, c);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                float dG = a.drop.apply(dx1[p][e], (size_t)row * a.D + c + e);
+                const float dG = dGv[e];
                 xh1[p][e] = (o2[e] - m1) * r1;
                 float n = xh1[p][e] * a.g1[c + e] + a.b1[c + e];
                 dzu[e] = dG * n * dsiluf(z2[e]);
@@ -304,15 +307,25 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
                                      const float* __restrict__ row_scale) {
     pdl_wait();
     drop.resolve();
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += stride) {
+    // a thread converts 4 neighbouring columns per step; (row, column) advance without divisions inside the loop
+    const size_t nq = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t D4 = (uint32_t)D / 4;
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // < 2^32 (the grid is capped), as is stride
+    uint32_t row = (uint32_t)q / D4, cq = (uint32_t)q % D4;
+    const uint32_t srow = (uint32_t)stride / D4, scq = (uint32_t)stride % D4;
+    for (; q < nq; q += stride) {
+        const size_t i = q * 4;
         float4 v = *reinterpret_cast<const float4*>(in + i);
-        float rs = row_scale ? row_scale[i / D] : 1.f;
+        const float rs = row_scale ? row_scale[row] : 1.f;
         uint2 o;
-        o.x = pack_bf16(drop.apply(v.x, i) * rs, drop.apply(v.y, i + 1) * rs);
-        o.y = pack_bf16(drop.apply(v.z, i + 2) * rs, drop.apply(v.w, i + 3) * rs);
+        drop.apply2(v.x, v.y, row, cq * 4);
+        drop.apply2(v.z, v.w, row, cq * 4 + 2);
+        o.x = pack_bf16(v.x * rs, v.y * rs);
+        o.y = pack_bf16(v.z * rs, v.w * rs);
         *reinterpret_cast<uint2*>(out + i) = o;
+        row += srow;
+        cq += scq;
+        if (cq >= D4) { cq -= D4; ++row; }
     }
 }
 // out[c] += sum_r in[r, c]   in: bf16 [T, ld] (ld % 8 == 0), columns [0, N) ; grid (ceil(N/256), chunks) ;
@@ -391,7 +404,11 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_fwd_kernel(EmbedArgs a) {
             }
             size_t o = (size_t)row * a.D + c;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = a.drop.apply(e[k], o + k) * keep;
+            for (int k = 0; k < 4; k += 2) {
+                a.drop.apply2(e[k], e[k + 1], row, c + k);
+                e[k] *= keep;
+                e[k + 1] *= keep;
+            }
             *reinterpret_cast<float4*>(a.x + o) = make_float4(e[0], e[1], e[2], e[3]);
         }
     }
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) 
         if (id == 0 && (a.mask_pad_rows || !a.dpos)) continue;
         for (int c = lane; c < a.D; c += 32) {
             size_t o = (size_t)row * a.D + c;
-            float gvl = a.drop.apply(a.dx[o], o);
+            float gvl = a.drop.apply(a.dx[o], row, c);
             if (id != 0) atomicAdd(a.dE + (size_t)id * a.D + c, gvl * a.scale);
             if (a.dpos && !(a.mask_pad_rows && id == 0)) atomicAdd(a.dpos + (size_t)(row % a.L) * a.D + c, gvl);
         }

@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     const float m_new = fmaxf(m_run, cm);
                     if (m_new > -INFINITY) {
                         float cs = 0.f;
+                        const float m2 = m_new * kLog2e;   // exp(v - m) = 2^(v * log2e - m * log2e): one FFMA + one MUFU per logit
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) cs += __expf(v[i] - m_new);
+                        for (int i = 0; i < 32; ++i) cs += ex2_fast(fmaf(v[i], kLog2e, -m2));
                         s_run = s_run * __expf(m_run - m_new) + cs;
                         m_run = m_new;
                     }
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             const float mm = fmaxf(mh, pp.x);
             const float ssum = ((mh == -INFINITY) ? 0.f : sh_ * __expf(mh - mm)) + ((pp.x == -INFINITY) ? 0.f : pp.y * __expf(pp.x - mm));
             const float lse = mm + __logf(ssum);
+            const float gshift = lse * kLog2e - __log2f(icr);   // icr == 0 (ignored row) -> +inf -> every gradient entry is 2^-inf = 0
             // loss: half 0 / quarter 0 adds lse - logit[target] once per row
             float contrib = (half == 0 && cq == 0) ? (lse - (tlh + pp.z)) * icr : 0.f;
             contrib = warp_sum(contrib);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + cq * 32), v);
                     const int col0 = n * 128 + cq * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __expf(v[i] - lse) * icr;
+                    for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // softmax * (1/count), folded into the exponent
                     if (col0 + 32 > sh.C) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)

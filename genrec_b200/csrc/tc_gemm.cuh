@@ -415,7 +415,6 @@ struct TcEpiBiasAct {
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
     GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&w)[32], int nvalid) const {
-        const size_t o = (size_t)row * ld + col0;
         float bb[32];
         load_f32x32(bias + col0, bb, nvalid);
 #pragma unroll
@@ -424,9 +423,12 @@ struct TcEpiBiasAct {
             v[i] = zz;
             if (ACT != 0) {
                 float zr = bf16_round(zz);
-                float av = ACT == 1 ? siluf(zr) : fmaxf(zr, 0.f);
-                w[i] = drop.apply(av, o + i);
+                w[i] = ACT == 1 ? siluf(zr) : fmaxf(zr, 0.f);
             }
+        }
+        if (ACT != 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) drop.apply2p(w[i], w[i + 1], row, (col0 >> 1) + (i >> 1));
         }
     }
 };
@@ -442,13 +444,16 @@ struct TcEpiBiasResidual {
     GRB_DEVINL void prepare() { drop.resolve(); }
     GRB_DEVINL void preload(int row, int col0, int nvalid, float (&r)[32]) const { load_f32x32(res + (size_t)row * ld + col0, r, nvalid); }
     GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&r)[32]) const {
-        const size_t o = (size_t)row * ld + col0;
         const float s = row_scale ? row_scale[row] : 1.f;
-#pragma unroll
         float bb[32];
         load_f32x32(bias + col0, bb, nvalid);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (r[i] + drop.apply(v[i] + bb[i], o + i)) * s;
+        for (int i = 0; i < 32; i += 2) {
+            float y0 = v[i] + bb[i], y1 = v[i + 1] + bb[i + 1];
+            drop.apply2p(y0, y1, row, (col0 >> 1) + (i >> 1));
+            v[i] = (r[i] + y0) * s;
+            v[i + 1] = (r[i + 1] + y1) * s;
+        }
     }
 };
 // g = dropmask(acc) * ACT'(z) -> bf16
@@ -462,11 +467,11 @@ struct TcEpiDAct {
     GRB_DEVINL void prepare() { drop.resolve(); }
     GRB_DEVINL void preload(int row, int col0, int nvalid, float (&zz)[32]) const { load_bf16x32(z + (size_t)row * ld + col0, zz, nvalid); }
     GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&zz)[32]) const {
-        const size_t o = (size_t)row * ld + col0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float d = ACT == 1 ? dsiluf(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
-            v[i] = drop.apply(v[i], o + i) * d;
+        for (int i = 0; i < 32; i += 2) {
+            drop.apply2p(v[i], v[i + 1], row, (col0 >> 1) + (i >> 1));
+            v[i] *= ACT == 1 ? dsiluf(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
+            v[i + 1] *= ACT == 1 ? dsiluf(zz[i + 1]) : (zz[i + 1] > 0.f ? 1.f : 0.f);
         }
     }
 };
