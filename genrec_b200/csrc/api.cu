@@ -339,6 +339,17 @@ int cast_bf16(const float* in, bf16* out, size_t n, int D, const Dropout& drop, 
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
+int cast_colsum(const float* in, bf16* out, int T, int D, const Dropout& drop, float* colsum_out, cudaStream_t st) {
+    GRB_REQUIRE(D > 0 && D % 4 == 0, "cast needs rows of a multiple-of-4 length D");
+    int cx = (D + 127) / 128;
+    int cy = (8 * sm_count() + cx - 1) / cx;
+    int maxy = (T + 31) / 32;
+    if (cy > maxy) cy = maxy;
+    if (cy < 1) cy = 1;
+    launch_k(cast_colsum_f32_bf16_kernel, dim3(cx, cy), 256, 0, st, in, out, T, D, drop, colsum_out);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
 int colsum(const bf16* in, int T, int N, int ld, float* out, cudaStream_t st) {
     if (N % 8 != 0 || ld % 8 != 0) return fail(GRB_EINVAL, "colsum needs N and ld to be multiples of 8");
     int cx = (N + 255) / 256;
@@ -441,8 +452,7 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
     const Dropout drop_gate = make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_GATE), d->seed_dev);
 
     // FFN second linear
-    GRB_TRY(cast_bf16(dy, w.dyb, (size_t)T * D, D, drop_out, nullptr, st));
-    GRB_TRY(colsum(w.dyb, T, D, D, g->ffn2_b, st));
+    GRB_TRY(cast_colsum(dy, w.dyb, T, D, drop_out, g->ffn2_b, st));   // dyb = bf16(dropmask(dy)) ; db2 += column sums
     {
         if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, st));  // dW2[D,4D] += dyb^T h
     }
@@ -500,7 +510,7 @@ int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int
     GRB_REQUIRE(B > 0 && L > 0 && B <= 65535 && L <= 65535, "bad shape B=%d L=%d", B, L);
     GRB_REQUIRE(ld_index >= L && ld_index % 8 == 0, "ld_index must be a multiple of 8 and >= L");
     GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS && npos >= 1 && npos <= ATT_MAX_BUCKETS, "bucket counts out of range");
-    dim3 grid((ld_index + 255) / 256, L, B);
+    dim3 grid((ld_index + 255) / 256, (L + 7) / 8, B);
     launch_k(hstu_bias_index_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(timestamps), pad,
                                                                                  reinterpret_cast<const long long*>(time_thr), pos_bucket, L,
                                                                                  ld_index, npos, ntime, out);

@@ -61,7 +61,9 @@ GRB_DEVINL int time_bucket_dev(long long dt, const long long* thr, int ntime) {
     return min(b, ntime - 1);
 }
 
-// out[b, i, j] = (j <= i && !pad[b, j]) ? pos_bucket[i - j] * 64 + bucket(|ts[b,i] - ts[b,j]|) : npos * 64      grid (ceil(ld/256), L, B)
+// out[b, i, j] = (j <= i && !pad[b, j]) ? pos_bucket[i - j] * 64 + bucket(|ts[b,i] - ts[b,j]|) : npos * 64
+// grid (ceil(ld / 256), ceil(L / 8), B), block 256 = 8 query rows x 32 threads ; a thread produces 8 neighbouring key
+// columns and writes them with one 16-byte store (ld % 8 == 0).
 __global__ void __launch_bounds__(256) hstu_bias_index_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad,
                                                              const long long* __restrict__ thr_g, const uint8_t* __restrict__ pos_bucket,
                                                              int L, int ld, int npos, int ntime, uint16_t* __restrict__ out) {
@@ -69,15 +71,25 @@ __global__ void __launch_bounds__(256) hstu_bias_index_kernel(const long long* _
     __shared__ long long thr[ATT_MAX_BUCKETS + 1];
     for (int i = threadIdx.x; i <= ATT_MAX_BUCKETS; i += 256) thr[i] = thr_g[i];
     __syncthreads();
-    const int b = blockIdx.z, i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= ld) return;
+    const int b = blockIdx.z, i = blockIdx.y * 8 + (threadIdx.x >> 5), j0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
+    if (i >= L || j0 >= ld) return;
     const size_t row = (size_t)b * L;
-    unsigned v = (unsigned)npos * 64u;
-    if (j <= i && j < L && pad[row + j] == 0) {
-        const unsigned tb = (ts != nullptr && ntime > 0) ? (unsigned)time_bucket_dev(ts[row + i] - ts[row + j], thr, ntime) : 0u;
-        v = (unsigned)pos_bucket[i - j] * 64u + tb;
+    const unsigned masked = (unsigned)npos * 64u;
+    const bool timed = ts != nullptr && ntime > 0;
+    const long long ti = timed ? ts[row + i] : 0;
+    unsigned v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = j0 + k;
+        v[k] = masked;
+        if (j <= i && pad[row + j] == 0) {     // j <= i < L
+            const unsigned tb = timed ? (unsigned)time_bucket_dev(ti - ts[row + j], thr, ntime) : 0u;
+            v[k] = (unsigned)pos_bucket[i - j] * 64u + tb;
+        }
     }
-    out[(row + i) * ld + j] = (uint16_t)v;
+    uint4 o;
+    o.x = v[0] | (v[1] << 16); o.y = v[2] | (v[3] << 16); o.z = v[4] | (v[5] << 16); o.w = v[6] | (v[7] << 16);
+    *reinterpret_cast<uint4*>(out + (row + i) * ld + j0) = o;
 }
 
 template <int DH>

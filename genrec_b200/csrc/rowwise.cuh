@@ -328,6 +328,50 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
         if (cq >= D4) { cq -= D4; ++row; }
     }
 }
+// out_bf16[r, c] = bf16(dropmask(in[r, c]))  and  colsum[c] += sum_r out_bf16[r, c]   (the cast of dy and the bias gradient
+// of the layer's last linear in one pass).  grid (ceil(D / 128), chunks) ; block 256 = 8 row lanes x 32 threads of 4 columns.
+__global__ void __launch_bounds__(256) cast_colsum_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int T, int D,
+                                                                  Dropout drop, float* __restrict__ colsum) {
+    pdl_wait();
+    drop.resolve();
+    __shared__ float red[8][128];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + 4 * tx;
+    const int rows_per = (T + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(T, r0 + rows_per);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < D) {
+        auto one = [&](int r, float4 v) {
+            drop.apply2(v.x, v.y, r, c);
+            drop.apply2(v.z, v.w, r, c + 2);
+            uint2 o;
+            o.x = pack_bf16(v.x, v.y);
+            o.y = pack_bf16(v.z, v.w);
+            *reinterpret_cast<uint2*>(out + (size_t)r * D + c) = o;
+            const float2 a = unpack_bf16(o.x), b = unpack_bf16(o.y);
+            s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y;
+        };
+        int r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const float4*>(in + (size_t)(r + 8 * u) * D + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one(r + 8 * u, q[u]);
+        }
+        for (; r < r1; r += 8) one(r, *reinterpret_cast<const float4*>(in + (size_t)r * D + c));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[ty][4 * tx + k] = s[k];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < D) atomicAdd(colsum + cc, t);
+    }
+}
 // out[c] += sum_r in[r, c]   in: bf16 [T, ld] (ld % 8 == 0), columns [0, N) ; grid (ceil(N/256), chunks) ;
 // block 256 = 32 column groups of 8 (one 16-byte load each) x 8 row lanes, 4 rows in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ in, int T, int N, int ld, float* __restrict__ out) {
@@ -442,7 +486,8 @@ __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* 
     pdl_wait();
     __shared__ int red[32];
     int c = 0;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;   // unrolled: the loads of a thread are in flight together
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
     __syncthreads();
