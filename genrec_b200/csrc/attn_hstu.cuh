@@ -316,6 +316,10 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
 
     const int i0 = q0 + warp * 16 + g, i1 = i0 + 8;
     const bool warp_live = q0 + warp * 16 < L;
+    {   // the epilogue multiplies by silu'(zq) of the warp's 16 query rows: pull those row segments towards L2 now
+        const int ir = q0 + warp * 16 + (lane & 15);
+        if (a.zq != nullptr && lane < 16 && ir < L) prefetch_l2(a.zq + (size_t)(tok0 + ir) * a.ldz + h * DH);
+    }
     uint32_t qf[DH / 16][4], dof[DH / 16][4];
     float dq[DH / 8][4];
 #pragma unroll
@@ -398,7 +402,7 @@ struct AttSmemKV {
     uint16_t ix[2][ATT_BLK * ATT_IX_LD];
 };
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int table_bytes) {
+__global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int table_bytes) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmemKV<DH>& sm = *reinterpret_cast<AttSmemKV<DH>*>(att_smem_raw);
@@ -439,6 +443,11 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
     __syncthreads();  // K/V fragments are in registers: stream buffer 1 may now be refilled
     const int j0 = k0 + warp * 16 + g, j1 = j0 + 8;
     const bool warp_live = k0 + warp * 16 < L;
+    {   // the epilogue multiplies by silu'(z) of the warp's 16 key rows: pull those 64-byte row segments towards L2 now
+        const int jr = k0 + warp * 16 + (lane & 15);
+        const bf16* zsrc = (lane < 16) ? a.zk : a.zv;
+        if (zsrc != nullptr && jr < L) prefetch_l2(zsrc + (size_t)(tok0 + jr) * a.ldz + h * DH);
+    }
     float dk[DH / 8][4], dv[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n)
@@ -541,6 +550,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) v += hist_p[(w * (npos + 1) + bk) * 32 + lane];
+            if (!__any_sync(0xffffffffu, v != 0.f)) continue;   // most bins of a tile are empty: skip their reductions
             v = warp_sum(v);
             if (lane == 0 && v != 0.f) atomicAdd(a.dwpos + bk * a.H + h, v);
         }
@@ -550,6 +560,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dkdv_kernel(HstuAtt
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) v += hist_t[(w * ntime + bk) * 32 + lane];
+            if (!__any_sync(0xffffffffu, v != 0.f)) continue;   // a tile touches ~10 of the 64 time buckets
             v = warp_sum(v);
             if (lane == 0 && v != 0.f) atomicAdd(a.dwtime + bk * a.H + h, v);
         }

@@ -167,6 +167,7 @@ GRB_DEVINL void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
                  "r"(src_bytes));
 }
+GRB_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 GRB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 GRB_DEVINL void cp_async_wait() {
