@@ -239,7 +239,7 @@ HstuAttnArgs make_attn_args(const grb_hstu_dims* d, const grb_hstu_layer_params*
 
 template <int DH>
 int launch_hstu_attn_fwd(const HstuAttnArgs& a, cudaStream_t st) {
-    size_t smem = sizeof(AttSmem<DH>) + align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);
+    size_t smem = sizeof(AttSmem<DH, 1>) + align_up((size_t)(a.bias.npos * 64 + 1) * 4, 16);
     GRB_TRY(set_smem(hstu_attn_fwd_kernel<DH>, smem));
     dim3 grid((a.L + ATT_BLK - 1) / ATT_BLK, a.H, a.B);
     launch_k(hstu_attn_fwd_kernel<DH>, grid, ATT_THREADS, smem, st, a);
@@ -292,9 +292,17 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
         launch_k(hstu_attn_bwd_dq_kernel<DH>, grid, ATT_THREADS, smem_q, st, a);
         GRB_CUDA(cudaGetLastError());
     }
-    size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + (a.bias.pos_uniform ? 0 : a.bias.npos + 1)) * 32 * sizeof(float);
-    GRB_TRY(set_smem(hstu_attn_bwd_dkdv_kernel<DH>, smem_k));
-    launch_k(hstu_attn_bwd_dkdv_kernel<DH>, grid, ATT_THREADS, smem_k, st, a, (int)posb);
+    size_t smem_k = sizeof(AttSmemKV<DH>) + posb + (size_t)4 * (a.bias.ntime + 1 + (a.bias.pos_uniform ? 0 : a.bias.npos + 1)) * 32 * sizeof(float);
+    const bool has_time = a.bias.wtime != nullptr && a.bias.ntime > 0, pos_uni = a.bias.pos_uniform != 0;
+    auto go = [&](auto kern) -> int {
+        GRB_TRY(set_smem(kern, smem_k));
+        launch_k(kern, grid, ATT_THREADS, smem_k, st, a, (int)posb);
+        return 0;
+    };
+    if (has_time && pos_uni) GRB_TRY(go(hstu_attn_bwd_dkdv_kernel<DH, true, true>));
+    else if (has_time) GRB_TRY(go(hstu_attn_bwd_dkdv_kernel<DH, true, false>));
+    else if (pos_uni) GRB_TRY(go(hstu_attn_bwd_dkdv_kernel<DH, false, true>));
+    else GRB_TRY(go(hstu_attn_bwd_dkdv_kernel<DH, false, false>));
     GRB_CUDA(cudaGetLastError());
     if (forked) GRB_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
     return 0;

@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(256) hstu_bias_index_kernel(const long long* _
     *reinterpret_cast<uint4*>(out + (row + i) * ld + j0) = o;
 }
 
-template <int DH>
+template <int DH, int NFIXED = 2>
 struct AttSmem {
     static constexpr int LD = DH + 8;
-    bf16 fixed[2][ATT_BLK * LD];      // the CTA's own rows (Q [+ dO]  or  K, V)
+    bf16 fixed[NFIXED][ATT_BLK * LD]; // the CTA's own rows: Q (forward, NFIXED = 1: 44 KB -> five CTAs per SM at dh = 32) or Q, dO
     bf16 stream[2][2][ATT_BLK * LD];  // [buffer][operand] streamed tiles
     uint16_t ix[2][ATT_BLK * ATT_IX_LD];  // [buffer] index tile: [query row][key col]
 };
@@ -202,11 +202,11 @@ GRB_DEVINL void att_pack_p(uint32_t (&pf)[4][4], const float (&s)[8][4]) {
 // ============================================================================================ forward
 // fixed[0] = Q ; stream[buf] = {K, V}
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 5 : 3) hstu_attn_fwd_kernel(HstuAttnArgs a) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
-    AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
-    float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH>));
+    AttSmem<DH, 1>& sm = *reinterpret_cast<AttSmem<DH, 1>*>(att_smem_raw);
+    float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmem<DH, 1>));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, q0 = qt * ATT_BLK;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_fwd_kernel(HstuAttnArgs
 // ============================================================================================ backward: dQ
 // fixed = {Q, dO} ; stream[buf] = {K, V}
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 4 : 2) hstu_attn_bwd_dq_kernel(HstuAttnArgs a) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
     AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(att_smem_raw);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(ATT_THREADS) hstu_attn_bwd_dq_kernel(HstuAttnA
 // ============================================================================================ backward: dK, dV, bias tables
 // CTA owns 64 keys: fixed = {K, V} ; stream[buf] = {Q, dO}
 // K and V are only needed as register fragments, so they are staged through stream buffer 1 before the main loop.
-// dynamic smem tail: wcomb[npos*64+1] (padded to 16 B) then LANE-PRIVATE histograms hist_t[4][ntime][32], hist_p[4][npos][32]
+// dynamic smem tail: wcomb[npos*64+1] (padded to 16 B) then LANE-PRIVATE histograms hist_t[4][ntime+1][32], hist_p[4][npos+1][32]
 // (each lane owns one 4-byte column: plain read-modify-write, bank-conflict free, no atomics; hist_p only when the
 // position buckets are not uniform)
 template <int DH>
@@ -401,7 +401,8 @@ struct AttSmemKV {
     bf16 stream[2][2][ATT_BLK * LD];
     uint16_t ix[2][ATT_BLK * ATT_IX_LD];
 };
-template <int DH>
+// HAS_TIME / POS_UNI are compile-time so that the per-cell histogram code carries no branches
+template <int DH, bool HAS_TIME, bool POS_UNI>
 __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_dkdv_kernel(HstuAttnArgs a, int table_bytes) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char att_smem_raw[];
@@ -409,18 +410,18 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
     float* wcomb = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmemKV<DH>));
     float* hist_t = reinterpret_cast<float*>(att_smem_raw + sizeof(AttSmemKV<DH>) + table_bytes);
     const int ntime = a.bias.ntime, npos = a.bias.npos;
-    float* hist_p = hist_t + 4 * ntime * 32;
+    const int nt_bins = ntime + 1;   // + one spare bin: masked cells of the uniform-position layout index it with an exact 0
+    float* hist_p = hist_t + 4 * nt_bins * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int L = a.L, k0 = kt * ATT_BLK;
     const long long tok0 = (long long)b * L;
-    const bool has_time = a.bias.wtime != nullptr && ntime > 0;
-    const bool pos_uniform = a.bias.pos_uniform != 0;
+    constexpr bool has_time = HAS_TIME, pos_uniform = POS_UNI;
     const int nqt = (L + ATT_BLK - 1) / ATT_BLK;
     const unsigned sentinel = (unsigned)npos * 64u;
 
     att_build_table(wcomb, a.bias, h, a.H, tid);
-    for (int i = tid; i < 4 * (ntime + (pos_uniform ? 0 : npos + 1)) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
+    for (int i = tid; i < 4 * (nt_bins + (pos_uniform ? 0 : npos + 1)) * 32; i += ATT_THREADS) hist_t[i] = 0.f;
     const bf16* gq = a.q + (size_t)tok0 * a.ldq + h * DH;
     const bf16* gdo = a.d_o + (size_t)tok0 * a.lddo + h * DH;
     const bf16* gk = a.k + (size_t)tok0 * a.ldk + h * DH;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
     for (int n = 0; n < DH / 8; ++n)
 #pragma unroll
         for (int r = 0; r < 4; ++r) dk[n][r] = 0.f, dv[n][r] = 0.f;
-    float* my_ht = hist_t + (warp * ntime) * 32 + lane;
+    float* my_ht = hist_t + (warp * nt_bins) * 32 + lane;
     float* my_hp = hist_p + (warp * (npos + 1)) * 32 + lane;   // bin `npos` only ever receives the zeros of masked cells
     float pos_acc = 0.f;  // sum of dS when all cells share one position bucket
 
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
                         st[n][r] = x * sg;
                         dat[n][r] = dsv;
                         // masked cells carry dsv == 0 exactly and index a valid (spare) bin, so no branch is needed
-                        if (has_time) my_ht[(id & 63u) * 32] += dsv;
+                        if (has_time) my_ht[(pos_uniform ? id : (id & 63u)) * 32] += dsv;   // uniform layout: id = time bucket, 64 = masked
                         if (!pos_uniform) my_hp[(id >> 6) * 32] += dsv;
                         pos_acc += dsv;
                     }
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
         for (int bk = warp; bk < ntime; bk += 4) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) v += hist_t[(w * ntime + bk) * 32 + lane];
+            for (int w = 0; w < 4; ++w) v += hist_t[(w * nt_bins + bk) * 32 + lane];
             if (!__any_sync(0xffffffffu, v != 0.f)) continue;   // a tile touches ~10 of the 64 time buckets
             v = warp_sum(v);
             if (lane == 0 && v != 0.f) atomicAdd(a.dwtime + bk * a.H + h, v);
