@@ -152,7 +152,7 @@ GRB_DEVINL void att_load_afrag(uint32_t (&f)[DH / 16][4], const bf16* tile, int 
 }
 
 // acc[8][4] (16 rows x 64 cols) = Afrag(16 x DH) * Tile^T   where Tile is [64][DH] (k = DH contiguous); only the first
-// `npairs` pairs of 8-column blocks are computed (warp-uniform)
+// `npairs` pairs of 8-column blocks are computed (warp-uniform), the others are set to 0.  acc is OVERWRITTEN.
 template <int DH>
 GRB_DEVINL void att_mma_nt(float (&acc)[8][4], const uint32_t (&af)[DH / 16][4], const bf16* tile, int lane, int npairs = 4) {
     constexpr int LD = DH + 8;
@@ -163,8 +163,16 @@ GRB_DEVINL void att_mma_nt(float (&acc)[8][4], const uint32_t (&af)[DH / 16][4],
             if (j2 < npairs) {
                 uint32_t r[4];
                 ldsm_x4(r, tile + (j2 * 16 + lane_b_row(lane)) * LD + ks * 16 + lane_b_col(lane));
-                mma_bf16(acc[2 * j2], af[ks], r[0], r[1]);
-                mma_bf16(acc[2 * j2 + 1], af[ks], r[2], r[3]);
+                if (ks == 0) {
+                    mma_bf16_z(acc[2 * j2], af[ks], r[0], r[1]);
+                    mma_bf16_z(acc[2 * j2 + 1], af[ks], r[2], r[3]);
+                } else {
+                    mma_bf16(acc[2 * j2], af[ks], r[0], r[1]);
+                    mma_bf16(acc[2 * j2 + 1], af[ks], r[2], r[3]);
+                }
+            } else if (ks == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[2 * j2][r] = 0.f, acc[2 * j2 + 1][r] = 0.f;
             }
         }
     }
@@ -482,6 +490,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
             att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane, kb1);   // S^T  = K Q^T   (rows = keys, cols = queries)
             att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane, kb1);  // dA^T = V dO^T
             const uint16_t* ix = sm.ix[buf];
+            // pass 1 - independent per cell (the compiler interleaves the 32 chains): A^T and dS^T in place
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 if (n >= nb0 && n < nb1) {
@@ -495,14 +504,30 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
                         const float dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));   // exactly 0 on masked cells
                         st[n][r] = x * sg;
                         dat[n][r] = dsv;
-                        // masked cells carry dsv == 0 exactly and index a valid (spare) bin, so no branch is needed
-                        if (has_time) my_ht[(pos_uniform ? id : (id & 63u)) * 32] += dsv;   // uniform layout: id = time bucket, 64 = masked
-                        if (!pos_uniform) my_hp[(id >> 6) * 32] += dsv;
                         pos_acc += dsv;
                     }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
+                }
+            }
+            // pass 2 - bias-table gradients: scatter dS into the lane-private histograms.  Kept apart from pass 1 because
+            // the read-modify-writes may alias each other (two cells of a lane often share a bucket) and would otherwise
+            // serialise the whole element-wise chain behind them.  Masked cells carry dS == 0 exactly and index a valid
+            // (spare) bin, so no branch is needed.
+            if (has_time || !pos_uniform) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    if (n >= nb0 && n < nb1) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int il = n * 8 + 2 * t + (r & 1);
+                            const int jl = warp * 16 + g + ((r < 2) ? 0 : 8);
+                            const unsigned id = ix[il * ATT_IX_LD + jl];
+                            if (has_time) my_ht[(pos_uniform ? id : (id & 63u)) * 32] += dat[n][r];   // uniform layout: id = time bucket, 64 = masked
+                            if (!pos_uniform) my_hp[(id >> 6) * 32] += dat[n][r];
+                        }
+                    }
                 }
             }
             uint32_t pf[4][4];

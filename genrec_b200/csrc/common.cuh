@@ -193,6 +193,14 @@ GRB_DEVINL void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uin
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// d = a * b (no accumulator input: the zero C operand becomes RZ, so callers need not clear d first)
+GRB_DEVINL void mma_bf16_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};\n"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 // Fragment address helpers (lane -> row/col of the 8x8 matrix row this lane points at), see DESIGN.md "mma.sync fragments".
 // A operand, smem tile stored [m][k] (k contiguous): non-transposed ldmatrix.
 GRB_DEVINL int lane_a_row(int lane) { return (lane & 7) + ((lane >> 3) & 1) * 8; }
