@@ -368,8 +368,12 @@ def block_roofline(model, B, L, dev, K):
     model.zero_grad(set_to_none=False)
     flops = (72 * L * D * D + 6 * D * L * (L + 1)) * B * nl
     ach = flops / (ms * 1e-3) / 1e12
+    # DRAM bytes (read + write) of the block stack's kernels for one fwd+bwd at the default geometry, summed from the ncu
+    # capture profiles/r1_step_dram_traffic.txt (scripts/step_traffic.py); not re-measured here (needs a profiler)
+    traffic = 2.106e9 if (B, L, D, nl) == (128, 200, 128, 4) else None
     return dict(bound="tensor", kernel="hstu_block_stack_fwd_bwd", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                peak_source=which, traffic=None, ms_per_launch=ms, flops_per_launch=flops,
+                peak_source=which, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                algorithmic_bytes_per_launch=(10 * L * D + 9 * L) * B * nl, ms_per_launch=ms, flops_per_launch=flops,
                 unit_of_work=f"{nl} layers x B={B} sequences x L={L}")
 
 
