@@ -47,6 +47,7 @@ P = C.POINTER
 SIGNATURES = {
     "grb_last_error": (C.c_char_p, []),
     "grb_version": (c_int, []),
+    "grb_launch_count": (c_u64, []),
     "grb_check_device": (c_int, [c_int]),
     "grb_hstu_layer_saved_bytes": (c_size_t, [P(HstuDims)]),
     "grb_hstu_layer_workspace_bytes": (c_size_t, [P(HstuDims)]),
@@ -146,8 +147,9 @@ def ensure_device(device: torch.device) -> None:
 
 
 def count_launches(n: int) -> None:
-    _loaded_count["launches"] += n
+    """Kept for call-site compatibility: the exact count now comes from the library itself (grb_launch_count)."""
 
 
 def launches() -> int:
-    return _loaded_count["launches"]
+    """CUDA kernels launched by libgenrec_b200.so in this process (counted inside its single launch helper)."""
+    return int(load().grb_launch_count()) if _lib is not None or os.path.exists(LIB_PATH) else 0

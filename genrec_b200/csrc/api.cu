@@ -379,6 +379,7 @@ extern "C" {
 
 const char* grb_last_error(void) { return g_err; }
 int grb_version(void) { return 100; }
+uint64_t grb_launch_count(void) { return (uint64_t)launch_counter(); }
 
 int grb_check_device(int ordinal) {
     cudaDeviceProp prop;

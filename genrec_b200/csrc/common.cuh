@@ -35,6 +35,11 @@ inline bool pdl_enabled() {
     return v != 0;
 }
 
+// every kernel launch of the library goes through launch_k, which also counts them (grb_launch_count in the C ABI)
+inline unsigned long long& launch_counter() {
+    static unsigned long long n = 0;
+    return n;
+}
 // launch_k(kernel, grid, block, smem, st, args...) with the PDL attribute (GRB_PDL=0 turns it off).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -49,6 +54,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    ++launch_counter();
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -32,6 +32,8 @@ extern "C" {
 
 const char* grb_last_error(void);
 int grb_version(void);
+/* number of CUDA kernels this library has launched in this process so far (host-side count at launch / graph-capture time) */
+uint64_t grb_launch_count(void);
 /* 0 when device `ordinal` is compute capability 10.x, GRB_ENODEV otherwise (host call). */
 int grb_check_device(int ordinal);
 
