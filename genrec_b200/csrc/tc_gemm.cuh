@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]          MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2; // [2]          epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* zfull_bar = bars + 2 * TC_STAGES + 5;  // [2]          TMA -> epilogue (auxiliary operand tile, Epi::kAux)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epi.prepare();
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TC_EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(&zfull_bar[a], 1);
         }
         fence_barrier_init();
     }
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int split = w % sh.splits;
                 const int tile = w / sh.splits;
@@ -212,6 +216,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         tma_load_2d(b_dst + TC_TILE_BYTES / 2, &tmB, n0 + 64, k0, &full_bar[stage]);
                     }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if constexpr (Epi::kAux) {
+                    // auxiliary element-wise operand of this tile -> the unused half of the tile's staging buffer, as soon as
+                    // the epilogue that last used that buffer (two tiles ago) has drained it
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    unsigned char* z_dst = sOut0 + acc * TC_STAGE_OUT_BYTES + 32768;
+                    mbar_expect_tx(&zfull_bar[acc], 32768);
+                    tma_load_2d(z_dst, &tmC1, n0, m0, &zfull_bar[acc]);                  // box {64 cols, 128 rows}
+                    tma_load_2d(z_dst + 16384, &tmC1, n0 + 64, m0, &zfull_bar[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
         }
@@ -274,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
+            if constexpr (Epi::kAux) mbar_wait(&zfull_bar[acc], acc_phase);
 #pragma unroll
             for (int ci = 0; ci < TC_EPI_CPW; ++ci) {
                 const int c = cq * TC_EPI_CPW + ci;
@@ -285,7 +300,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (row < sh.M && nvalid > 0) epi(row, col0, v, nvalid);
                 } else {
                     float w[32];
-                    if constexpr (Epi::kPre) {
+                    if constexpr (Epi::kAux) {
+                        // this thread's 32 bf16 of the auxiliary tile (same 128B-swizzled box layout as the bf16 staging tile)
+                        float zz[32];
+                        const unsigned char* zsrc = sOut + 32768 + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(zsrc + ((((c & 1) * 4 + j) ^ (r & 7)) << 4));
+                            const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                            zz[8 * j] = f0.x; zz[8 * j + 1] = f0.y; zz[8 * j + 2] = f1.x; zz[8 * j + 3] = f1.y;
+                            zz[8 * j + 4] = f2.x; zz[8 * j + 5] = f2.y; zz[8 * j + 6] = f3.x; zz[8 * j + 7] = f3.y;
+                        }
+                        if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid, zz);
+                    } else if constexpr (Epi::kPre) {
                         if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid, pre[ci]);
                     } else {
                         if (row < sh.M && nvalid > 0) epi(row, col0, v, w, nvalid);
@@ -410,6 +437,7 @@ template <int ACT>
 struct TcEpiBiasAct {
     static constexpr int kOut = ACT == 0 ? 1 : 2;   // tmC0 = z, tmC1 = act
     static constexpr bool kPre = false;
+    static constexpr bool kAux = false;
     const float* bias;
     int ld;
     Dropout drop;
@@ -436,6 +464,7 @@ struct TcEpiBiasAct {
 struct TcEpiBiasResidual {
     static constexpr int kOut = 3;
     static constexpr bool kPre = true;
+    static constexpr bool kAux = false;
     const float* bias;
     const float* res;
     const float* row_scale;
@@ -460,12 +489,12 @@ struct TcEpiBiasResidual {
 template <int ACT>
 struct TcEpiDAct {
     static constexpr int kOut = 1;
-    static constexpr bool kPre = true;
+    static constexpr bool kPre = false;
+    static constexpr bool kAux = true;   // the saved pre-activation tile z[128 x 128] arrives by TMA (tensor map in the kernel's tmC1 slot)
     const bf16* z;
     int ld;
     Dropout drop;
     GRB_DEVINL void prepare() { drop.resolve(); }
-    GRB_DEVINL void preload(int row, int col0, int nvalid, float (&zz)[32]) const { load_bf16x32(z + (size_t)row * ld + col0, zz, nvalid); }
     GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&zz)[32]) const {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -479,6 +508,7 @@ struct TcEpiDAct {
 struct TcEpiF32 {
     static constexpr int kOut = 3;
     static constexpr bool kPre = true;
+    static constexpr bool kAux = false;
     const float* res;
     int ld;
     float scale;
@@ -500,6 +530,7 @@ struct TcEpiF32 {
 struct TcEpiAtomicF32 {
     static constexpr int kOut = 0;
     static constexpr bool kPre = false;
+    static constexpr bool kAux = false;
     float* out;
     int ld;
     float scale;
@@ -515,6 +546,7 @@ struct TcEpiAtomicF32 {
 struct TcEpiBf16 {
     static constexpr int kOut = 1;
     static constexpr bool kPre = false;
+    static constexpr bool kAux = false;
     GRB_DEVINL void prepare() {}
     GRB_DEVINL void operator()(int, int, float (&)[32], float (&)[32], int) const {}
 };
@@ -522,6 +554,7 @@ struct TcEpiBf16 {
 struct TcEpiF32Plain {
     static constexpr int kOut = 0;
     static constexpr bool kPre = false;
+    static constexpr bool kAux = false;
     float* out;
     int ld;
     GRB_DEVINL void prepare() {}
@@ -581,6 +614,10 @@ inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, in
         ok = ok && make_tmap(&tmC0, out0, false, M, N, ldo, 64, TC_BM);
         if (Epi::kOut == 2) ok = ok && make_tmap(&tmC1, out1, false, M, N, ldo, 64, TC_BM);
         else tmC1 = tmC0;
+    }
+    if constexpr (Epi::kAux) {
+        static_assert(Epi::kOut == 1, "the auxiliary tile lives in the half of the staging buffer a single bf16 output leaves free");
+        ok = ok && make_tmap(&tmC1, epi.z, false, M, N, epi.ld, 64, TC_BM);
     }
     if (!ok) return cudaErrorInvalidValue;
     TcGemmShape sh;
