@@ -223,6 +223,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + cq * 32), v);
+                    // the accumulator is in registers: hand it back to the MMA warp before the element-wise work
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
                     const int col0 = n * 128 + cq * 32;
                     if (col0 + 32 > sh.C) {
 #pragma unroll
@@ -247,9 +251,6 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         m_run = m_new;
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             // combine the four column quarters of every row (this half of the classes) ...
@@ -296,6 +297,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 128 + cq * 32), v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained (it lives in registers now)
                     const int col0 = n * 128 + cq * 32;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // softmax * (1/count), folded into the exponent
@@ -318,9 +322,6 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         *reinterpret_cast<uint4*>(dst + ((((cq & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 fence_proxy_async();   // generic-proxy smem writes -> visible to TMA and to tcgen05.mma (async proxy)
                 ce_bar_sync();
