@@ -16,6 +16,7 @@
 #include "rq_argmin.cuh"
 #include "tc_gemm.cuh"
 #include "tc_ce.cuh"
+#include "tc_ffn.cuh"
 #include "tc_tn_group.cuh"
 #include <cstdlib>
 
@@ -358,6 +359,14 @@ int cast_colsum(const float* in, bf16* out, int T, int D, const Dropout& drop, f
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
+// GRB_FFN_FUSED=1 routes the forward FFN through the single fused kernel of tc_ffn.cuh.  Off by default: at cfg-2 it
+// measures 47 us per layer against 43 us for the two separate GEMM launches (its 16 epilogue warps walk the phases of a
+// chunk in lock-step); it is the first building block of the fused layer kernel and is kept bit-compatible and tested.
+// Read on every call so that a test can flip it.
+bool ffn_fused() {
+    const char* e = getenv("GRB_FFN_FUSED");
+    return e != nullptr && e[0] == '1';
+}
 int colsum(const bf16* in, int T, int N, int ld, float* out, cudaStream_t st) {
     if (N % 8 != 0 || ld % 8 != 0) return fail(GRB_EINVAL, "colsum needs N and ld to be multiples of 8");
     int cx = (N + 255) / 256;
@@ -430,6 +439,15 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
         LnGateFwdArgs a{sv.O, D, sv.P, 4 * D, x, p->ln1_g, p->ln1_b, p->ln2_g, p->ln2_b, sv.x1, sv.xn, sv.st1, sv.st2, T, D, 1e-5f,
                         make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_GATE), d->seed_dev)};
         GRB_ROW_DISPATCH(D, ln_gate_fwd_kernel, a, T, st);
+    }
+    // 5 + 6 in one kernel (tc_ffn.cuh): h is written once for the backward and never re-read in the forward
+    if (use_tc() && ffn_fused() && (D == 64 || D == 128)) {
+        FfnEpiArgs ea{p->ffn1_b, p->ffn2_b, sv.x1, sv.z1, y,
+                      make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_HID), d->seed_dev),
+                      make_dropout(d->dropout_p, d->seed, site_of(d->layer_index, SITE_FFN_OUT), d->seed_dev)};
+        if (D == 64) GRB_CUDA(launch_tc_ffn_fwd<1>(sv.xn, (const bf16*)p->ffn1_w, (const bf16*)p->ffn2_w, sv.hact, T, ea, sm_count(), st));
+        else GRB_CUDA(launch_tc_ffn_fwd<2>(sv.xn, (const bf16*)p->ffn1_w, (const bf16*)p->ffn2_w, sv.hact, T, ea, sm_count(), st));
+        return 0;
     }
     // 5. h = drop(silu(xn W1^T + b1))                                                        (hstu.py:210-212)
     {

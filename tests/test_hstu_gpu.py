@@ -183,3 +183,32 @@ def test_cpu_tensors_raise():
     m = HSTU(50, 20, 64, 2, 1, dropout=0.0)
     with pytest.raises(RuntimeError):
         m(torch.randint(1, 50, (2, 5)))
+
+
+@pytest.mark.parametrize("D,H", [(64, 2), (128, 4)])
+def test_fused_ffn_kernel_matches_the_two_gemm_path(D, H, monkeypatch):
+    """GRB_FFN_FUSED=1 runs LN2 -> W1 -> SiLU -> dropout -> W2 -> residual as one tcgen05 kernel (csrc/tc_ffn.cuh); outputs,
+    the tensors saved for the backward, and therefore every gradient must equal the default two-launch path (same
+    accumulation order, same dropout masks)."""
+    from genrec_b200.hstu import HSTULayer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    B, L = 5, 77          # T = 385: three full row blocks + a ragged one
+    layer = HSTULayer(D, H, 0.2, 32, 64, 128, True).to(dev).train()
+    x = torch.randn(B, L, D, device=dev)
+    ts = (1_300_000_000 + torch.cumsum(torch.randint(1, 86400, (B, L), device=dev), 1))
+    pad = torch.zeros(B, L, dtype=torch.bool, device=dev)
+    dy = torch.randn(B, L, D, device=dev)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("GRB_FFN_FUSED", flag)
+        layer.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        y = layer(xi, None, pad, ts, _seed=1234)
+        y.backward(dy)
+        outs.append((y.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in layer.parameters() if p.grad is not None]))
+    (y0, dx0, g0), (y1, dx1, g1) = outs
+    torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dx1, dx0, rtol=1e-4, atol=1e-5)
+    for a, b in zip(g1, g0):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-4 * max(1.0, b.abs().max().item()))
