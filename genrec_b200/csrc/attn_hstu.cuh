@@ -197,6 +197,11 @@ GRB_DEVINL void att_mma_nn(float (&out)[DH / 8][4], const uint32_t (&pf)[4][4], 
     }
 }
 
+template <bool B>
+struct FullTile {
+    static constexpr bool value = B;
+};
+
 GRB_DEVINL void att_pack_p(uint32_t (&pf)[4][4], const float (&s)[8][4]) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -258,28 +263,31 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 5 : 3) hstu_attn_fwd_k
         if (warp_live) {
             int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;  // 8-key blocks intersecting this warp's causal triangle
             nblk = min(nblk, (L - kt * ATT_BLK + 7) >> 3);       // ... and lying below L
-            const int npairs = (nblk + 1) >> 1;
-            float s[8][4];
+            const int npairs_rt = (nblk + 1) >> 1;
+            // FULL: the whole 64-key tile is visible to this warp (every tile but the diagonal and the last one) - no
+            // per-block guards, so the 32 score chains of a lane are one straight-line block the scheduler can interleave
+            auto tile = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
+                const int npairs = FULL ? 4 : npairs_rt;
+                float s[8][4];
+                att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);
+                const uint16_t* ix = sm.ix[buf];
 #pragma unroll
-            for (int n = 0; n < 8; ++n)
+                for (int n = 0; n < 8; ++n) {
+                    if (FULL || n < 2 * npairs) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) s[n][r] = 0.f;
-            att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);
-            const uint16_t* ix = sm.ix[buf];
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                if (n < 2 * npairs) {
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
-                        s[n][2 * hf] = siluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);
-                        s[n][2 * hf + 1] = siluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
+                            s[n][2 * hf] = siluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);
+                            s[n][2 * hf + 1] = siluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
+                        }
                     }
                 }
-            }
-            uint32_t pf[4][4];
-            att_pack_p(pf, s);
-            att_mma_nn<DH>(o, pf, sm.stream[buf][1], lane, 0, npairs);
+                uint32_t pf[4][4];
+                att_pack_p(pf, s);
+                att_mma_nn<DH>(o, pf, sm.stream[buf][1], lane, 0, npairs);
+            };
+            if (npairs_rt == 4) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();  // everyone done with buffer `buf` before it is refilled two iterations later
     }
@@ -352,29 +360,30 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 4 : 2) hstu_attn_bwd_d
         if (warp_live) {
             int nblk = (kt == qt) ? min(8, 2 * warp + 2) : 8;
             nblk = min(nblk, (L - kt * ATT_BLK + 7) >> 3);
-            const int npairs = (nblk + 1) >> 1;
-            float s[8][4], da[8][4];
+            const int npairs_rt = (nblk + 1) >> 1;
+            auto tile = [&](auto full_c) {     // FULL: no per-block guards (see the forward kernel)
+                constexpr bool FULL = decltype(full_c)::value;
+                const int npairs = FULL ? 4 : npairs_rt;
+                float s[8][4], da[8][4];
+                att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);    // S  = Q K^T
+                att_mma_nt<DH>(da, dof, sm.stream[buf][1], lane, npairs);  // dA = dO V^T
+                const uint16_t* ix = sm.ix[buf];
 #pragma unroll
-            for (int n = 0; n < 8; ++n)
+                for (int n = 0; n < 8; ++n) {
+                    if (FULL || n < 2 * npairs) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) s[n][r] = 0.f, da[n][r] = 0.f;
-            att_mma_nt<DH>(s, qf, sm.stream[buf][0], lane, npairs);    // S  = Q K^T
-            att_mma_nt<DH>(da, dof, sm.stream[buf][1], lane, npairs);  // dA = dO V^T
-            const uint16_t* ix = sm.ix[buf];
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                if (n < 2 * npairs) {
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
-                        s[n][2 * hf] = da[n][2 * hf] * dsiluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);              // dS
-                        s[n][2 * hf + 1] = da[n][2 * hf + 1] * dsiluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t i2 = *reinterpret_cast<const uint32_t*>(ix + (warp * 16 + g + 8 * hf) * ATT_IX_LD + n * 8 + 2 * t);
+                            s[n][2 * hf] = da[n][2 * hf] * dsiluf(s[n][2 * hf] + wcomb[i2 & 0xffffu]);              // dS
+                            s[n][2 * hf + 1] = da[n][2 * hf + 1] * dsiluf(s[n][2 * hf + 1] + wcomb[i2 >> 16]);
+                        }
                     }
                 }
-            }
-            uint32_t pf[4][4];
-            att_pack_p(pf, s);
-            att_mma_nn<DH>(dq, pf, sm.stream[buf][0], lane, 0, npairs);  // dQ += dS K
+                uint32_t pf[4][4];
+                att_pack_p(pf, s);
+                att_mma_nn<DH>(dq, pf, sm.stream[buf][0], lane, 0, npairs);  // dQ += dS K
+            };
+            if (npairs_rt == 4) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();
     }
@@ -478,63 +487,64 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
         __syncthreads();
         if (warp_live) {
             // query 8-blocks that can see this warp's keys (diagonal tile: queries >= first key of the warp)
-            const int nb0 = (qt == kt) ? 2 * warp : 0;  // first live 8-query block (warp-uniform, even)
-            const int kb0 = nb0 >> 1;                    // first live k16 block for the second GEMMs
-            const int nb1 = min(8, (L - qt * ATT_BLK + 7) >> 3);   // query blocks at or beyond L hold nothing (last tile of a short sequence)
-            const int kb1 = (nb1 + 1) >> 1;
-            float st[8][4], dat[8][4];
-#pragma unroll
-            for (int n = 0; n < 8; ++n)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
-            att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane, kb1);   // S^T  = K Q^T   (rows = keys, cols = queries)
-            att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane, kb1);  // dA^T = V dO^T
-            const uint16_t* ix = sm.ix[buf];
-            // pass 1 - independent per cell (the compiler interleaves the 32 chains): A^T and dS^T in place
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                if (n >= nb0 && n < nb1) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int il = n * 8 + 2 * t + (r & 1);
-                        const int jl = warp * 16 + g + ((r < 2) ? 0 : 8);
-                        const unsigned id = ix[il * ATT_IX_LD + jl];
-                        const float x = st[n][r] + wcomb[id];
-                        const float sg = sigmoidf_fast(x);
-                        const float dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));   // exactly 0 on masked cells
-                        st[n][r] = x * sg;
-                        dat[n][r] = dsv;
-                        pos_acc += dsv;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
-                }
-            }
-            // pass 2 - bias-table gradients: scatter dS into the lane-private histograms.  Kept apart from pass 1 because
-            // the read-modify-writes may alias each other (two cells of a lane often share a bucket) and would otherwise
-            // serialise the whole element-wise chain behind them.  Masked cells carry dS == 0 exactly and index a valid
-            // (spare) bin, so no branch is needed.
-            if (has_time || !pos_uniform) {
+            const int nb0_rt = (qt == kt) ? 2 * warp : 0;  // first live 8-query block (warp-uniform, even)
+            const int nb1_rt = min(8, (L - qt * ATT_BLK + 7) >> 3);   // query blocks at or beyond L hold nothing (last tile of a short sequence)
+            auto tile = [&](auto full_c) {     // FULL: all 8 query blocks are live - no per-block guards (see the forward kernel)
+                constexpr bool FULL = decltype(full_c)::value;
+                const int nb0 = FULL ? 0 : nb0_rt, nb1 = FULL ? 8 : nb1_rt;
+                const int kb0 = nb0 >> 1;                    // first live k16 block for the second GEMMs
+                const int kb1 = (nb1 + 1) >> 1;
+                float st[8][4], dat[8][4];
+                att_mma_nt<DH>(st, kf, sm.stream[buf][0], lane, kb1);   // S^T  = K Q^T   (rows = keys, cols = queries)
+                att_mma_nt<DH>(dat, vf, sm.stream[buf][1], lane, kb1);  // dA^T = V dO^T
+                const uint16_t* ix = sm.ix[buf];
+                // pass 1 - independent per cell (the compiler interleaves the chains): A^T and dS^T in place
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                    if (n >= nb0 && n < nb1) {
+                    if (FULL || (n >= nb0 && n < nb1)) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             const int il = n * 8 + 2 * t + (r & 1);
                             const int jl = warp * 16 + g + ((r < 2) ? 0 : 8);
                             const unsigned id = ix[il * ATT_IX_LD + jl];
-                            if (has_time) my_ht[(pos_uniform ? id : (id & 63u)) * 32] += dat[n][r];   // uniform layout: id = time bucket, 64 = masked
-                            if (!pos_uniform) my_hp[(id >> 6) * 32] += dat[n][r];
+                            const float x = st[n][r] + wcomb[id];
+                            const float sg = sigmoidf_fast(x);
+                            const float dsv = dat[n][r] * (sg * (1.f + x * (1.f - sg)));   // exactly 0 on masked cells
+                            st[n][r] = x * sg;
+                            dat[n][r] = dsv;
+                            pos_acc += dsv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) st[n][r] = 0.f, dat[n][r] = 0.f;
+                    }
+                }
+                // pass 2 - bias-table gradients: scatter dS into the lane-private histograms.  Kept apart from pass 1 because
+                // the read-modify-writes may alias each other (two cells of a lane often share a bucket) and would otherwise
+                // serialise the whole element-wise chain behind them.  Masked cells carry dS == 0 exactly and index a valid
+                // (spare) bin, so no branch is needed.
+                if (has_time || !pos_uniform) {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        if (FULL || (n >= nb0 && n < nb1)) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int il = n * 8 + 2 * t + (r & 1);
+                                const int jl = warp * 16 + g + ((r < 2) ? 0 : 8);
+                                const unsigned id = ix[il * ATT_IX_LD + jl];
+                                if (has_time) my_ht[(pos_uniform ? id : (id & 63u)) * 32] += dat[n][r];   // uniform layout: id = time bucket, 64 = masked
+                                if (!pos_uniform) my_hp[(id >> 6) * 32] += dat[n][r];
+                            }
                         }
                     }
                 }
-            }
-            uint32_t pf[4][4];
-            att_pack_p(pf, st);
-            att_mma_nn<DH>(dv, pf, sm.stream[buf][1], lane, kb0, kb1);  // dV += A^T dO
-            att_pack_p(pf, dat);
-            att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, kb1);  // dK += dS^T Q
+                uint32_t pf[4][4];
+                att_pack_p(pf, st);
+                att_mma_nn<DH>(dv, pf, sm.stream[buf][1], lane, kb0, kb1);  // dV += A^T dO
+                att_pack_p(pf, dat);
+                att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, kb1);  // dK += dS^T Q
+            };
+            if (nb0_rt == 0 && nb1_rt == 8) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();
     }
