@@ -25,6 +25,14 @@ namespace grb {
 constexpr int ATT_BLK = 64;       // rows per CTA and per streamed tile
 constexpr int ATT_THREADS = 128;  // 4 warps x 16 rows
 constexpr int ATT_MAX_BUCKETS = 64;
+// Diagonal tiles that lie wholly below L also take the guard-free straight-line path: their masked (above-diagonal) cells are
+// computed and come out as exact zeros through the sentinel index, which costs up to half a tile of wasted work but lets
+// the scheduler interleave all 32 score chains of a lane.  Measured at cfg-2: 1.923 -> 1.889 ms per step.  (-DGRB_ATT_DIAG_FULL=0
+// restores the per-warp triangular skipping.)
+#ifndef GRB_ATT_DIAG_FULL
+#define GRB_ATT_DIAG_FULL 1
+#endif
+constexpr bool ATT_DIAG_FULL = GRB_ATT_DIAG_FULL != 0;
 constexpr int ATT_IX_LD = ATT_BLK + 8;  // padded row (uint16 elements) of the index tile in smem: 144 B, conflict-free
 constexpr float ATT_MASK_BIAS = -30000.f;
 
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 5 : 3) hstu_attn_fwd_k
                 att_pack_p(pf, s);
                 att_mma_nn<DH>(o, pf, sm.stream[buf][1], lane, 0, npairs);
             };
-            if (npairs_rt == 4) tile(FullTile<true>{}); else tile(FullTile<false>{});
+            if (npairs_rt == 4 || (ATT_DIAG_FULL && (kt + 1) * ATT_BLK <= L)) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();  // everyone done with buffer `buf` before it is refilled two iterations later
     }
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 4 : 2) hstu_attn_bwd_d
                 att_pack_p(pf, s);
                 att_mma_nn<DH>(dq, pf, sm.stream[buf][0], lane, 0, npairs);  // dQ += dS K
             };
-            if (npairs_rt == 4) tile(FullTile<true>{}); else tile(FullTile<false>{});
+            if (npairs_rt == 4 || (ATT_DIAG_FULL && (kt + 1) * ATT_BLK <= L)) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();
     }
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(ATT_THREADS, DH == 32 ? 3 : 2) hstu_attn_bwd_d
                 att_pack_p(pf, dat);
                 att_mma_nn<DH>(dk, pf, sm.stream[buf][0], lane, kb0, kb1);  // dK += dS^T Q
             };
-            if (nb0_rt == 0 && nb1_rt == 8) tile(FullTile<true>{}); else tile(FullTile<false>{});
+            if ((nb0_rt == 0 || ATT_DIAG_FULL) && nb1_rt == 8) tile(FullTile<true>{}); else tile(FullTile<false>{});
         }
         __syncthreads();
     }
