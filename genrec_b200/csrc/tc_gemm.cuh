@@ -7,7 +7,7 @@
 //   Both majors map straight onto UMMA shared-memory descriptors (K-major / MN-major canonical SWIZZLE_128B layouts),
 //   so no operand is ever transposed in memory.
 //
-// Persistent kernel, one CTA per SM, 192 threads:
+// Persistent kernel, one CTA per SM, 320 threads:
 //   warp 0    : TMA producer (one elected lane)      - ring of TC_STAGES x (A 16 KB + B 16 KB)
 //   warp 1    : TMEM allocator + MMA issuer (one lane): 4 x tcgen05.mma (K = 16 each) per 64-wide k-block
 //   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 = 32 rows of the 128 x 128 tile and, by (w-2)/4, one
