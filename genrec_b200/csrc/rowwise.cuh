@@ -486,8 +486,16 @@ __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* 
     pdl_wait();
     __shared__ int red[32];
     int c = 0;
-#pragma unroll 8
-    for (int i = threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;   // unrolled: the loads of a thread are in flight together
+    // 16-byte loads, deeply unrolled: all loads of a thread are in flight together (this single-CTA kernel is one DRAM
+    // round trip long instead of one per target)
+    const longlong2* tg2 = reinterpret_cast<const longlong2*>(tg);
+    const int T2 = ((reinterpret_cast<uintptr_t>(tg) & 15) == 0) ? T / 2 : 0;
+#pragma unroll 16
+    for (int i = threadIdx.x; i < T2; i += blockDim.x) {
+        const longlong2 v = tg2[i];
+        c += (v.x != 0) + (v.y != 0);
+    }
+    for (int i = 2 * T2 + threadIdx.x; i < T; i += blockDim.x) c += tg[i] != 0;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
     __syncthreads();
