@@ -559,6 +559,8 @@ int grb_embed_forward(const int64_t* ids, const float* table, const float* pos_t
 int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float* dpos_table, int B, int L, int D, float scale,
                        int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
     GRB_REQUIRE(ids && dx && dtable, "null argument");
+    GRB_REQUIRE(D % 4 == 0 && aligned16(dx) && aligned16(dtable) && (dpos_table == nullptr || aligned16(dpos_table)),
+                "embedding backward needs D %% 4 == 0 and 16-byte aligned buffers");
     EmbedBwdArgs a{reinterpret_cast<const long long*>(ids), dx, dtable, dpos_table, B * L, L, D, scale, mask_pad_rows,
                    make_dropout(dropout_p, seed, SITE_EMBED, seed_dev)};
     launch_k(embed_bwd_kernel, row_grid(B * L), ROW_THREADS, 0, static_cast<cudaStream_t>(stream), a);

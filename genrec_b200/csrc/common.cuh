@@ -173,6 +173,10 @@ GRB_DEVINL void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
                  "r"(src_bytes));
 }
+// 16-byte vector reduction into global fp32 (address 16-byte aligned): one L2 atomic transaction for four elements
+GRB_DEVINL void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 GRB_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 GRB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>

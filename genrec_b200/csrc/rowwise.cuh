@@ -471,11 +471,13 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) 
     for (int row = blockIdx.x * (ROW_THREADS / 32) + wib; row < a.T; row += nw) {
         long long id = a.ids[row];
         if (id == 0 && (a.mask_pad_rows || !a.dpos)) continue;
-        for (int c = lane; c < a.D; c += 32) {
-            size_t o = (size_t)row * a.D + c;
-            float gvl = a.drop.apply(a.dx[o], row, c);
-            if (id != 0) atomicAdd(a.dE + (size_t)id * a.D + c, gvl * a.scale);
-            if (a.dpos && !(a.mask_pad_rows && id == 0)) atomicAdd(a.dpos + (size_t)(row % a.L) * a.D + c, gvl);
+        // four columns per lane and one 16-byte vector reduction per destination (D % 4 == 0, rows 16-byte aligned)
+        for (int c = 4 * lane; c < a.D; c += 128) {
+            float4 v = *reinterpret_cast<const float4*>(a.dx + (size_t)row * a.D + c);
+            a.drop.apply2(v.x, v.y, row, c);
+            a.drop.apply2(v.z, v.w, row, c + 2);
+            if (id != 0) red_add_v4(a.dE + (size_t)id * a.D + c, v.x * a.scale, v.y * a.scale, v.z * a.scale, v.w * a.scale);
+            if (a.dpos && !(a.mask_pad_rows && id == 0)) red_add_v4(a.dpos + (size_t)(row % a.L) * a.D + c, v.x, v.y, v.z, v.w);
         }
     }
 }

@@ -26,9 +26,6 @@ struct TnGroupParams {
     int total_work;
 };
 
-GRB_DEVINL void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 struct TnItem {
     int prob, m0, n0, kb0, kb1;
