@@ -198,7 +198,7 @@ class HeadLossFn(torch.autograd.Function):
         xc = x.detach().contiguous().float()
         tg = targets.contiguous()
         need_grad = any(ctx.needs_input_grad[:4])
-        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)   # zeroed on the device by the target-count kernel
         ws = _u8(lib.grb_head_workspace_bytes(T, D, Cn), x.device)
         if need_grad and sink is not None:
             dx = torch.empty_like(xc)
