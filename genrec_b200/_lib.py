@@ -34,7 +34,8 @@ class HstuLayerGrads(C.Structure):
 
 
 class HstuSeq(C.Structure):
-    _fields_ = [("bias_index", c_void_p), ("ld_index", c_int), ("has_time", c_int), ("pos_uniform", c_int), ("pos_bucket0", c_int)]
+    _fields_ = [("bias_index", c_void_p), ("ld_index", c_int), ("has_time", c_int), ("pos_uniform", c_int), ("pos_bucket0", c_int),
+                ("timestamps", c_void_p), ("pad", c_void_p), ("rel32", c_void_p), ("wide", c_void_p), ("time_thr", c_void_p)]
 
 
 class SasrecDims(C.Structure):
@@ -55,6 +56,12 @@ SIGNATURES = {
     "grb_hstu_layer_backward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p,
                                         P(HstuLayerGrads), c_void_p, c_void_p]),
     "grb_hstu_bias_index": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "grb_hstu_seq_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "grb_hstu_bucket_bytes_debug": (c_int, [P(HstuSeq), c_int, c_int, c_int, c_void_p, c_void_p]),
+    "grb_hstu_attention_scratch_bytes": (c_size_t, [P(HstuDims)]),
+    "grb_hstu_attention_forward": (c_int, [P(HstuDims), c_void_p, c_void_p, P(HstuSeq), c_void_p, c_void_p, c_void_p]),
+    "grb_hstu_attention_backward": (c_int, [P(HstuDims), c_void_p, c_void_p, P(HstuSeq), c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "grb_embed_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                   c_float, c_u64, c_void_p, c_void_p]),
     "grb_embed_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float,
@@ -85,6 +92,7 @@ SIGNATURES = {
     "grb_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "grb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,
                               c_float, c_float, c_float, c_float, c_int, c_void_p]),
+    "grb_assert_unit_scalar": (c_int, [c_void_p, c_void_p]),
     "grb_rq_residual_argmin": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
 }
@@ -144,10 +152,6 @@ def ensure_device(device: torch.device) -> None:
         return
     check(load().grb_check_device(idx))
     _device_ok.add(idx)
-
-
-def count_launches(n: int) -> None:
-    """Kept for call-site compatibility: the exact count now comes from the library itself (grb_launch_count)."""
 
 
 def launches() -> int:

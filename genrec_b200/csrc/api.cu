@@ -7,9 +7,11 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <utility>
 
 #include "attn_hstu.cuh"
 #include "attn_sasrec.cuh"
+#include "attn_tc.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
@@ -52,15 +54,20 @@ int fail(int code, const char* fmt, ...) {
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+int sm_count() {     // per device ordinal: a process may drive several GPUs
+    static int n[64] = {0};
+    const int dev = current_device() & 63;
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 int row_grid(int T) {
     int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
@@ -168,7 +175,7 @@ LayerSaved carve_saved(void* base, size_t T, size_t D) {
 }
 struct LayerWork {
     bf16 *dyb, *dz1, *dO, *dzp;
-    float *dxn, *dx1;
+    float *dxn, *dx1, *dq_acc;
     size_t bytes;
 };
 LayerWork carve_work(void* base, size_t T, size_t D) {
@@ -182,6 +189,7 @@ LayerWork carve_work(void* base, size_t T, size_t D) {
     w.dx1 = (float*)take(T * D * 4);
     w.dO = (bf16*)take(T * D * 2);
     w.dzp = (bf16*)take(T * 4 * D * 2);
+    w.dq_acc = (float*)take(T * D * 4);
     w.bytes = off;
     return w;
 }
@@ -205,9 +213,9 @@ int check_dims(const grb_hstu_dims* d) {
 template <class Kern>
 int set_smem(Kern k, size_t bytes) {
     static std::mutex mu;
-    static std::map<const void*, size_t> high_water;  // keyed by kernel address (same-signature kernels share this instance)
+    static std::map<std::pair<int, const void*>, size_t> high_water;  // keyed by (device, kernel address): the attribute is per device
     std::lock_guard<std::mutex> lock(mu);
-    size_t& hw = high_water[reinterpret_cast<const void*>(k)];
+    size_t& hw = high_water[std::make_pair(current_device(), reinterpret_cast<const void*>(k))];
     if (hw < 48 * 1024) hw = 48 * 1024;
     if (bytes > hw) {
         GRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -306,6 +314,90 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
     else GRB_TRY(go(hstu_attn_bwd_dkdv_kernel<DH, false, false>));
     GRB_CUDA(cudaGetLastError());
     if (forked) GRB_CUDA(cudaStreamWaitEvent(st, ss.join, 0));
+    return 0;
+}
+
+// ---- tcgen05 attention path (attn_tc.cuh): the default whenever the position buckets are uniform (the reference's behaviour)
+//      and head_dim is 32 or 64.  GRB_ATTN=mma selects the first-generation mma.sync kernels (they need the bias_index matrix).
+bool attn_tc_enabled() {
+    const char* e = getenv("GRB_ATTN");   // read on every call so that a test can flip it
+    return !(e && strcmp(e, "mma") == 0);
+}
+bool use_attn_tc(const grb_hstu_dims* d, const grb_hstu_seq* s) {
+    const int dh = d->D / d->H;
+    return attn_tc_enabled() && s->pos_uniform && (dh == 32 || dh == 64) && d->D % 64 == 0 && s->pad != nullptr && s->time_thr != nullptr &&
+           (s->timestamps == nullptr || !s->has_time || (s->rel32 != nullptr && s->wide != nullptr));
+}
+HstuTcArgs make_tc_args(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s) {
+    HstuTcArgs a;
+    memset(&a, 0, sizeof(a));
+    const bool has_time = time_table != nullptr && s->has_time && s->timestamps != nullptr && d->ntime > 0;
+    a.ts = has_time ? reinterpret_cast<const long long*>(s->timestamps) : nullptr;
+    a.rel32 = has_time ? s->rel32 : nullptr;
+    a.wide = s->wide;
+    a.pad = s->pad;
+    a.thr64 = reinterpret_cast<const long long*>(s->time_thr);
+    a.wpos = pos_table + (size_t)s->pos_bucket0 * d->H;
+    a.wtime = has_time ? time_table : nullptr;
+    a.ntime = has_time ? d->ntime : 0;
+    a.B = d->B; a.L = d->L; a.H = d->H; a.D = d->D;
+    return a;
+}
+int launch_attn_tc_fwd(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s, const bf16* P, bf16* O,
+                       cudaStream_t st) {
+    const int D = d->D, dh = D / d->H;
+    const size_t T = (size_t)d->B * d->L;
+    HstuTcArgs a = make_tc_args(d, pos_table, time_table, s);
+    a.o = O; a.ldo = D;
+    CUtensorMap tmP;
+    if (!make_tmap_bf16(&tmP, P, T, 4 * (size_t)D, 4 * (size_t)D, 64, 128)) return fail(GRB_EINVAL, "tensor map creation failed (attention P)");
+    const int nqt = (d->L + 127) / 128;
+    const unsigned grid = (unsigned)((D / 64) * d->B * nqt);
+    if (dh == 32) {
+        const size_t smem = AtcFwdSmem<32>::kBytes + 1024;
+        GRB_TRY(set_smem(hstu_attn_tc_fwd_kernel<32>, smem));
+        launch_k(hstu_attn_tc_fwd_kernel<32>, grid, ATC_THREADS, smem, st, tmP, a, nqt);
+    } else {
+        const size_t smem = AtcFwdSmem<64>::kBytes + 1024;
+        GRB_TRY(set_smem(hstu_attn_tc_fwd_kernel<64>, smem));
+        launch_k(hstu_attn_tc_fwd_kernel<64>, grid, ATC_THREADS, smem, st, tmP, a, nqt);
+    }
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+// dzp columns V, Q, K <- gradients w.r.t. the pre-activations ; dq_acc: [T, D] fp32 scratch
+int launch_attn_tc_bwd(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s, const bf16* P,
+                       const bf16* zp, const bf16* dO, bf16* dzp, float* dwpos, float* dwtime, float* dq_acc, cudaStream_t st) {
+    const int D = d->D, dh = D / d->H;
+    const size_t T = (size_t)d->B * d->L;
+    HstuTcArgs a = make_tc_args(d, pos_table, time_table, s);
+    a.zk = zp ? zp + 3 * D : nullptr; a.zv = zp ? zp + D : nullptr; a.ldz = 4 * D;
+    a.dk = dzp + 3 * D; a.dv = dzp + D; a.lddz = 4 * D;
+    a.dq_acc = dq_acc;
+    a.dwpos = dwpos + (size_t)s->pos_bucket0 * d->H;
+    a.dwtime = a.wtime ? dwtime : nullptr;
+    GRB_REQUIRE(a.wtime == nullptr || dwtime != nullptr, "time_table gradient pointer is null");
+    CUtensorMap tmP, tmDO;
+    if (!make_tmap_bf16(&tmP, P, T, 4 * (size_t)D, 4 * (size_t)D, 64, 128) || !make_tmap_bf16(&tmDO, dO, T, D, D, 64, 128))
+        return fail(GRB_EINVAL, "tensor map creation failed (attention backward)");
+    GRB_CUDA(cudaMemsetAsync(dq_acc, 0, T * D * sizeof(float), st));
+    const int nqt = (d->L + 127) / 128;
+    const unsigned grid = (unsigned)((D / 64) * d->B * nqt);
+    if (dh == 32) {
+        const size_t smem = AtcBwdSmem<32>::kBytes + 1024;
+        GRB_TRY(set_smem(hstu_attn_tc_bwd_kernel<32>, smem));
+        launch_k(hstu_attn_tc_bwd_kernel<32>, grid, ATC_THREADS, smem, st, tmP, tmDO, a, nqt);
+    } else {
+        const size_t smem = AtcBwdSmem<64>::kBytes + 1024;
+        GRB_TRY(set_smem(hstu_attn_tc_bwd_kernel<64>, smem));
+        launch_k(hstu_attn_tc_bwd_kernel<64>, grid, ATC_THREADS, smem, st, tmP, tmDO, a, nqt);
+    }
+    GRB_CUDA(cudaGetLastError());
+    size_t blocks = (T * (D / 8) + 255) / 256;
+    if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+    launch_k(hstu_dq_finish_kernel, (unsigned)blocks, 256, 0, st, (const float*)dq_acc, zp ? zp + 2 * D : (const bf16*)nullptr, 4 * D, dzp + 2 * D,
+             4 * D, T, D);
+    GRB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -413,8 +505,10 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
     GRB_REQUIRE(p && s && x && y && saved, "null argument");
     GRB_REQUIRE(p->proj_w && p->proj_b && p->pos_table && p->ln1_g && p->ln1_b && p->ffn1_w && p->ffn1_b && p->ffn2_w &&
                     p->ffn2_b && p->ln2_g && p->ln2_b, "null parameter pointer");
-    GRB_REQUIRE(s->bias_index, "null sequence metadata");
-    GRB_REQUIRE(s->ld_index >= d->L && s->ld_index % 8 == 0 && aligned16(s->bias_index), "bias_index pitch must be a multiple of 8 and >= L");
+    const bool attn_tc = use_attn_tc(d, s);
+    GRB_REQUIRE(attn_tc || s->bias_index, "null sequence metadata: the mma.sync attention path needs bias_index");
+    GRB_REQUIRE(attn_tc || (s->ld_index >= d->L && s->ld_index % 8 == 0 && aligned16(s->bias_index)),
+                "bias_index pitch must be a multiple of 8 and >= L");
     GRB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(saved) && aligned16(p->proj_w) && aligned16(p->ffn1_w) && aligned16(p->ffn2_w),
                 "buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -429,7 +523,9 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
         GRB_CUDA(gemm_bias_act(1, sv.xb, (const bf16*)p->proj_w, p->proj_b, sv.zp, sv.P, T, 4 * D, D, nodrop, st));
     }
     // 3. O = silu(Q K^T + bias) V, causal + key padding                                      (hstu.py:244-267)
-    {
+    if (attn_tc) {
+        GRB_TRY(launch_attn_tc_fwd(d, p->pos_table, p->time_table, s, sv.P, sv.O, st));
+    } else {
         HstuAttnArgs a = make_attn_args(d, p, s, sv);
         if (D / d->H == 32) GRB_TRY(launch_hstu_attn_fwd<32>(a, st));
         else GRB_TRY(launch_hstu_attn_fwd<64>(a, st));
@@ -501,7 +597,10 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
         GRB_ROW_DISPATCH(D, ln_gate_bwd_kernel, a, T, st);
     }
     // attention backward -> gradients w.r.t. the V, Q, K pre-activations
-    {
+    if (use_attn_tc(d, s)) {
+        GRB_TRY(launch_attn_tc_bwd(d, p->pos_table, p->time_table, s, sv.P, sv.zp, w.dO, w.dzp, g->pos_table, g->time_table, w.dq_acc, st));
+    } else {
+        GRB_REQUIRE(s->bias_index, "null sequence metadata: the mma.sync attention path needs bias_index");
         HstuAttnArgs a = make_attn_args(d, p, s, sv);
         a.d_o = w.dO; a.lddo = D;
         a.zq = sv.zp + 2 * D; a.zk = sv.zp + 3 * D; a.zv = sv.zp + D; a.ldz = 4 * D;
@@ -543,6 +642,58 @@ int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int
                                                                                  ld_index, npos, ntime, out);
     GRB_CUDA(cudaGetLastError());
     return 0;
+}
+
+int grb_hstu_seq_prepare(const int64_t* timestamps, const uint8_t* pad, int B, int L, int32_t* rel32, uint8_t* wide, void* stream) {
+    GRB_REQUIRE(timestamps && pad && rel32 && wide, "null argument");
+    GRB_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
+    launch_k(hstu_seq_prep_kernel, (unsigned)B, 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(timestamps), pad, L,
+             reinterpret_cast<int*>(rel32), wide);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int grb_hstu_bucket_bytes_debug(const grb_hstu_seq* s, int B, int L, int ntime, uint8_t* out, void* stream) {
+    GRB_REQUIRE(s && out && s->pad && s->time_thr, "null argument");
+    GRB_REQUIRE(B > 0 && L > 0 && B <= 65535 && ntime >= 0 && ntime <= 64, "bad shape");
+    HstuTcArgs a;
+    memset(&a, 0, sizeof(a));
+    const bool has_time = s->timestamps != nullptr && s->has_time && ntime > 0;
+    GRB_REQUIRE(!has_time || (s->rel32 && s->wide), "rel32 / wide missing: call grb_hstu_seq_prepare first");
+    a.ts = has_time ? reinterpret_cast<const long long*>(s->timestamps) : nullptr;
+    a.rel32 = s->rel32; a.wide = s->wide; a.pad = s->pad;
+    a.thr64 = reinterpret_cast<const long long*>(s->time_thr);
+    a.ntime = has_time ? ntime : 0;
+    a.B = B; a.L = L;
+    dim3 grid((L + 31) / 32, (L + 127) / 128, B);
+    launch_k(hstu_bucket_bytes_debug_kernel, grid, 128, 0, static_cast<cudaStream_t>(stream), a, out);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t grb_hstu_attention_scratch_bytes(const grb_hstu_dims* d) {
+    if (check_dims(d)) return 0;
+    return align_up((size_t)d->B * d->L * d->D * sizeof(float));
+}
+int grb_hstu_attention_forward(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s,
+                               const void* P_bf16, void* O_bf16, void* stream) {
+    GRB_TRY(check_dims(d));
+    GRB_REQUIRE(pos_table && s && P_bf16 && O_bf16, "null argument");
+    GRB_REQUIRE(use_attn_tc(d, s), "the stand-alone attention entry points run the tcgen05 path: uniform position buckets, head_dim 32/64, "
+                                   "pad / time_thr (and rel32 / wide with timestamps) required");
+    GRB_REQUIRE(aligned16(P_bf16) && aligned16(O_bf16), "buffers must be 16-byte aligned");
+    return launch_attn_tc_fwd(d, pos_table, time_table, s, (const bf16*)P_bf16, (bf16*)O_bf16, static_cast<cudaStream_t>(stream));
+}
+int grb_hstu_attention_backward(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s,
+                                const void* P_bf16, const void* zp_bf16, const void* dO_bf16, void* dzp_bf16, float* dpos_table,
+                                float* dtime_table, void* scratch, void* stream) {
+    GRB_TRY(check_dims(d));
+    GRB_REQUIRE(pos_table && s && P_bf16 && dO_bf16 && dzp_bf16 && dpos_table && scratch, "null argument");
+    GRB_REQUIRE(use_attn_tc(d, s), "the stand-alone attention entry points run the tcgen05 path");
+    GRB_REQUIRE(aligned16(P_bf16) && aligned16(dO_bf16) && aligned16(dzp_bf16) && aligned16(scratch) && (zp_bf16 == nullptr || aligned16(zp_bf16)),
+                "buffers must be 16-byte aligned");
+    return launch_attn_tc_bwd(d, pos_table, time_table, s, (const bf16*)P_bf16, (const bf16*)zp_bf16, (const bf16*)dO_bf16, (bf16*)dzp_bf16,
+                              dpos_table, dtime_table, (float*)scratch, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ embedding
@@ -830,6 +981,22 @@ int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
     launch_k(adam_step_kernel, (unsigned)blocks, 256, 0, st, a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+namespace {
+__global__ void assert_unit_scalar_kernel(const float* v) {
+    pdl_wait();
+    if (*v != 1.0f) {
+        printf("genrec_b200: the loss was back-propagated with gradient %g, but FlatAdam(unit_loss_grad=True) promised 1\n", (double)*v);
+        __trap();
+    }
+}
+}  // namespace
+int grb_assert_unit_scalar(const float* value, void* stream) {
+    GRB_REQUIRE(value, "null argument");
+    launch_k(assert_unit_scalar_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), value);
     GRB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -392,7 +392,10 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
         if (me != cudaSuccess) return me;
     }
     auto kern = tc_ce_kernel<KB>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ce_smem_bytes<KB>());
         if (e != cudaSuccess) return e;

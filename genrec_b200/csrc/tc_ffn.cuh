@@ -318,7 +318,10 @@ inline cudaError_t launch_tc_ffn_fwd(const bf16* xn, const bf16* w1, const bf16*
     sh.T = T;
     sh.num_m = (T + 127) / 128;
     auto kern = tc_ffn_fwd_kernel<KB>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem<KB>::kBytes);
         if (e != cudaSuccess) return e;

@@ -630,7 +630,10 @@ inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, in
     sh.kblocks_per_split = (sh.kblocks_total + splits - 1) / splits;
     sh.splits = (sh.kblocks_total + sh.kblocks_per_split - 1) / sh.kblocks_per_split;
     auto kern = tc_gemm_kernel<A_MN, B_MN, Epi>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;

@@ -197,7 +197,10 @@ inline cudaError_t launch_tc_tn_group(const TnSpec* specs, int n, int num_sms, c
         work += tiles * q.splits;
     }
     P.total_work = work;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_tn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES);
         if (e != cudaSuccess) return e;

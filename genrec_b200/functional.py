@@ -6,6 +6,7 @@ Every function here hands raw device pointers + the current CUDA stream to ``lib
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -18,6 +19,19 @@ PARAM_ORDER = ("proj_w", "proj_b", "pos_table", "time_table", "ln1_g", "ln1_b", 
 BF16_PARAMS = ("proj_w", "ffn1_w", "ffn2_w")
 
 
+def require_f32(*tensors) -> None:
+    for t in tensors:
+        if t is not None and t.dtype != torch.float32:
+            raise _lib.GrbError(f"genrec_b200 error -1: parameters / activations must be float32 (got {t.dtype}); the kernels keep fp32 "
+                                "masters and make their own bf16 operand copies")
+
+
+def require_i64(*tensors) -> None:
+    for t in tensors:
+        if t is not None and t.dtype != torch.int64:
+            raise _lib.GrbError(f"genrec_b200 error -1: ids / targets / timestamps must be int64 (got {t.dtype})")
+
+
 def _u8(n, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
@@ -28,46 +42,88 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     src = src.detach().contiguous()
     if out is None:
         out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    check(_lib.load().grb_cast_f32_to_bf16(ptr(src), ptr(out), src.numel(), stream_ptr(src.device)))
-    _lib.count_launches(1)
+    require_f32(src)
+    with torch.cuda.device(src.device):
+        check(_lib.load().grb_cast_f32_to_bf16(ptr(src), ptr(out), src.numel(), stream_ptr(src.device)))
     return out
 
 
 _ZERO_TABLES = {}
 
 
+def attn_legacy() -> bool:
+    """GRB_ATTN=mma selects the first-generation mma.sync attention kernels (kept as an on-device cross-check)."""
+    return os.environ.get("GRB_ATTN", "") == "mma"
+
+
 class SeqMeta:
-    """Per-batch sequence metadata shared by all layers of one forward.  Builds the [B, L, ld] uint16 bias-index matrix
-    once (grb_hstu_bias_index) from the pad flags, the timestamps and the position-bucket table."""
+    """Per-batch sequence metadata shared by all layers of one forward.
+
+    tcgen05 attention path (default): the pad flags, the raw timestamps and their per-sequence int32 rebasing
+    (``grb_hstu_seq_prepare``, one tiny launch per batch) - buckets and masks are derived inside the attention kernels.
+    The [B, L, ld] uint16 bias-index matrix of the mma.sync path is built lazily, only when that path will run
+    (non-uniform position buckets, or GRB_ATTN=mma)."""
 
     def __init__(self, pad_u8: torch.Tensor, timestamps: Optional[torch.Tensor], pos_bucket: torch.Tensor,
                  time_thr: torch.Tensor, num_time_buckets: int = 64, num_pos_buckets: int = 32, pos_uniform=None):
         require_cuda(pad_u8)
         B, L = pad_u8.shape
+        self.B, self.L = B, L
         self.pad = pad_u8.contiguous()
+        if self.pad.dtype != torch.uint8:
+            raise _lib.GrbError("genrec_b200 error -1: pad flags must be uint8")
+        if timestamps is not None and timestamps.dtype != torch.int64:
+            raise _lib.GrbError(f"genrec_b200 error -1: timestamps must be int64, got {timestamps.dtype}")
         self.timestamps = timestamps.contiguous() if timestamps is not None else None
         self.pos_bucket = pos_bucket
+        self.time_thr = time_thr
+        self.num_time_buckets, self.num_pos_buckets = num_time_buckets, num_pos_buckets
         if pos_uniform is None:        # (uniform?, bucket) - a host-side property of the [L] table, cached by the caller
             pb = pos_bucket.cpu()
             pos_uniform = (bool((pb == pb[0]).all()), int(pb[0]))
         self.pos_uniform, self.pos_bucket0 = pos_uniform
         self.ld = (L + 7) // 8 * 8
-        self.bias_index = torch.empty(B, L, self.ld, dtype=torch.int16, device=pad_u8.device)
-        nt = num_time_buckets if self.timestamps is not None else 0
+        self.bias_index = None
+        self.rel32 = self.wide = None
+        dev = pad_u8.device
+        with torch.cuda.device(dev):
+            if self.timestamps is not None:
+                self.rel32 = torch.empty(B, L, dtype=torch.int32, device=dev)
+                self.wide = torch.empty(B, dtype=torch.uint8, device=dev)
+                check(_lib.load().grb_hstu_seq_prepare(ptr(self.timestamps), ptr(self.pad), B, L, ptr(self.rel32), ptr(self.wide),
+                                                       stream_ptr(dev)))
+            if not self.pos_uniform or attn_legacy():
+                self._build_bias_index()
+
+    def _build_bias_index(self):
+        B, L, dev = self.B, self.L, self.pad.device
+        self.bias_index = torch.empty(B, L, self.ld, dtype=torch.int16, device=dev)
+        nt = self.num_time_buckets if self.timestamps is not None else 0
         if self.pos_uniform:      # collapse to one effective position bucket (see grb_hstu_seq.pos_uniform)
-            key = (L, str(pad_u8.device))
+            key = (L, str(dev))
             if key not in _ZERO_TABLES:
-                _ZERO_TABLES[key] = torch.zeros(L, dtype=torch.uint8, device=pad_u8.device)
+                _ZERO_TABLES[key] = torch.zeros(L, dtype=torch.uint8, device=dev)
             pb_arg, npos_arg = _ZERO_TABLES[key], 1
         else:
-            pb_arg, npos_arg = pos_bucket, num_pos_buckets
-        check(_lib.load().grb_hstu_bias_index(ptr(self.timestamps), ptr(self.pad), ptr(time_thr), ptr(pb_arg), B, L,
-                                              npos_arg, nt, ptr(self.bias_index), self.ld, stream_ptr(pad_u8.device)))
-        _lib.count_launches(1)
+            pb_arg, npos_arg = self.pos_bucket, self.num_pos_buckets
+        check(_lib.load().grb_hstu_bias_index(ptr(self.timestamps), ptr(self.pad), ptr(self.time_thr), ptr(pb_arg), B, L,
+                                              npos_arg, nt, ptr(self.bias_index), self.ld, stream_ptr(dev)))
 
     def struct(self) -> HstuSeq:
+        if self.bias_index is None and attn_legacy():
+            self._build_bias_index()
         return HstuSeq(ptr(self.bias_index), self.ld, 1 if self.timestamps is not None else 0, 1 if self.pos_uniform else 0,
-                       self.pos_bucket0)
+                       self.pos_bucket0, ptr(self.timestamps), ptr(self.pad), ptr(self.rel32), ptr(self.wide), ptr(self.time_thr))
+
+    def bucket_bytes(self, num_time_buckets: Optional[int] = None) -> torch.Tensor:
+        """[B, L, L] uint8: the time bucket (or 64 = masked) the tcgen05 attention kernels derive for every cell (test hook)."""
+        nt = self.num_time_buckets if num_time_buckets is None else num_time_buckets
+        out = torch.full((self.B, self.L, self.L), 255, dtype=torch.uint8, device=self.pad.device)
+        seq = self.struct()
+        with torch.cuda.device(self.pad.device):
+            check(_lib.load().grb_hstu_bucket_bytes_debug(C.byref(seq), self.B, self.L, nt if self.timestamps is not None else 0, ptr(out),
+                                                          stream_ptr(self.pad.device)))
+        return out
 
 
 def _dims(B, L, D, H, npos, ntime, p, seed, seed_dev, layer) -> HstuDims:
@@ -85,6 +141,7 @@ class HstuLayerFn(torch.autograd.Function):
         B, L, D = x.shape
         xc = x.detach().contiguous().float()
         named = dict(zip(PARAM_ORDER, params))
+        require_f32(*[q for q in params if q is not None])
         has_time = named["time_table"] is not None and meta.timestamps is not None
         dims = _dims(B, L, D, cfg["H"], cfg["npos"], cfg["ntime"] if has_time else 0, cfg["p"], cfg["seed"], cfg["seed_dev"],
                      cfg["layer"])
@@ -97,9 +154,9 @@ class HstuLayerFn(torch.autograd.Function):
         saved = _u8(nbytes, x.device)
         y = torch.empty_like(xc)
         seq = meta.struct()
-        check(lib.grb_hstu_layer_forward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(xc), ptr(y), ptr(saved),
-                                         stream_ptr(x.device)))
-        _lib.count_launches(6)
+        with torch.cuda.device(x.device):
+            check(lib.grb_hstu_layer_forward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(xc), ptr(y), ptr(saved),
+                                             stream_ptr(x.device)))
         ctx.meta, ctx.cfg, ctx.bf16w, ctx.has_time = meta, cfg, bf16w, has_time
         ctx.saved_blob = saved
         ctx.shape = (B, L, D)
@@ -130,9 +187,9 @@ class HstuLayerFn(torch.autograd.Function):
         dx = torch.empty_like(dyc)
         ws = _u8(lib.grb_hstu_layer_workspace_bytes(C.byref(dims)), dy.device)
         seq = meta.struct()
-        check(lib.grb_hstu_layer_backward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(dyc), ptr(ctx.saved_blob), ptr(dx),
-                                          C.byref(gstruct), ptr(ws), stream_ptr(dy.device)))
-        _lib.count_launches(15)
+        with torch.cuda.device(dy.device):
+            check(lib.grb_hstu_layer_backward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(dyc), ptr(ctx.saved_blob), ptr(dx),
+                                              C.byref(gstruct), ptr(ws), stream_ptr(dy.device)))
         ctx.saved_blob = None
         if sink is not None:
             return (dx, None, None, None, *([None] * len(PARAM_ORDER)))
@@ -146,16 +203,18 @@ class EmbedFn(torch.autograd.Function):
     def forward(ctx, ids, table, pos_table, scale, mask_pad_rows, p, seed, seed_dev, sink=None):
         lib = _lib.load()
         require_cuda(ids, table)
+        require_i64(ids)
+        require_f32(table, pos_table)
         ctx.sink = sink
         B, L = ids.shape
         D = table.shape[1]
         ids = ids.contiguous()
         x = torch.empty(B, L, D, dtype=torch.float32, device=ids.device)
         pad = torch.empty(B, L, dtype=torch.uint8, device=ids.device)
-        check(lib.grb_embed_forward(ptr(ids), ptr(table.detach()), ptr(pos_table.detach()) if pos_table is not None else None,
-                                    ptr(x), ptr(pad), B, L, D, float(scale), int(mask_pad_rows), float(p), int(seed), ptr(seed_dev),
-                                    stream_ptr(ids.device)))
-        _lib.count_launches(1)
+        with torch.cuda.device(ids.device):
+            check(lib.grb_embed_forward(ptr(ids), ptr(table.detach()), ptr(pos_table.detach()) if pos_table is not None else None,
+                                        ptr(x), ptr(pad), B, L, D, float(scale), int(mask_pad_rows), float(p), int(seed), ptr(seed_dev),
+                                        stream_ptr(ids.device)))
         ctx.save_for_backward(ids)
         ctx.args = (table.shape, None if pos_table is None else pos_table.shape, scale, mask_pad_rows, p, seed, seed_dev)
         ctx.mark_non_differentiable(pad)
@@ -174,33 +233,42 @@ class EmbedFn(torch.autograd.Function):
         else:
             dtable = torch.zeros(tshape, dtype=torch.float32, device=dx.device)
             dpos = torch.zeros(pshape, dtype=torch.float32, device=dx.device) if pshape is not None else None
-        check(lib.grb_embed_backward(ptr(ids), ptr(dx), ptr(dtable), ptr(dpos), B, L, D, float(scale), int(mask_pad_rows), float(p),
-                                     int(seed), ptr(seed_dev), stream_ptr(dx.device)))
-        _lib.count_launches(1)
+        with torch.cuda.device(dx.device):
+            check(lib.grb_embed_backward(ptr(ids), ptr(dx), ptr(dtable), ptr(dpos), B, L, D, float(scale), int(mask_pad_rows), float(p),
+                                         int(seed), ptr(seed_dev), stream_ptr(dx.device)))
         if ctx.sink is not None:
             return (None,) * 9
         return None, dtable, dpos, None, None, None, None, None, None
 
 
 class HeadLossFn(torch.autograd.Function):
-    """loss = CE(LN(x) @ E^T, targets, ignore_index=0); gradients are produced in the same pass (the loss is a scalar,
-    so backward only rescales them by the incoming grad)."""
+    """loss = CE(LN(x) @ E^T, targets, ignore_index=0).  The fused kernel produces the gradients in the same pass as the loss;
+    ``backward`` scales them by the incoming gradient of the loss.
+
+    ``sink = (dln_g, dln_b, dtable)`` are views of the flat gradient buffer (genrec_b200.optim.FlatAdam).  The sink is only
+    ever touched in ``backward``: the head gradients wait in scratch tensors and are added as ``sink += dloss * grad`` - any
+    loss scaling (gradient accumulation, a GradScaler) reaches the head and embedding gradients exactly as it reaches the
+    layers through ``dx``, and a forward that is never back-propagated leaves the gradient buffer alone.
+    ``unit_loss_grad=True`` (opt-in, ``FlatAdam(..., unit_loss_grad=True)``) is the fast path of a plain ``loss.backward()``:
+    the kernels accumulate straight into the sink during this call and ``backward`` hands ``dx`` on unscaled; the contract
+    (the loss is back-propagated exactly once, with gradient 1) is checked ON THE DEVICE in ``backward`` - a violation traps."""
 
     @staticmethod
-    def forward(ctx, x, ln_g, ln_b, table, table_bf16, targets, eps, sink=None):
-        """sink = (dln_g, dln_b, dtable) views of the flat gradient buffer: parameter gradients are accumulated there
-        during this call, ASSUMING the loss is back-propagated exactly once with gradient 1 (FlatAdam contract)."""
+    def forward(ctx, x, ln_g, ln_b, table, table_bf16, targets, eps, sink=None, unit_loss_grad=False):
         lib = _lib.load()
-        ctx.sink = sink
         require_cuda(x, table, targets)
+        require_i64(targets)
+        require_f32(ln_g, ln_b, table)
         B, L, D = x.shape
         T, Cn = B * L, table.shape[0]
         xc = x.detach().contiguous().float()
         tg = targets.contiguous()
         need_grad = any(ctx.needs_input_grad[:4])
+        direct = need_grad and sink is not None and unit_loss_grad
+        ctx.sink, ctx.direct = sink, direct
         loss = torch.empty((), dtype=torch.float32, device=x.device)   # zeroed on the device by the target-count kernel
         ws = _u8(lib.grb_head_workspace_bytes(T, D, Cn), x.device)
-        if need_grad and sink is not None:
+        if direct:
             dx = torch.empty_like(xc)
             dg, db, dtable = sink
         elif need_grad:
@@ -210,10 +278,10 @@ class HeadLossFn(torch.autograd.Function):
             db = torch.zeros_like(ln_b, dtype=torch.float32)
         else:
             dx = dtable = dg = db = None
-        check(lib.grb_head_loss_forward_backward(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), ptr(tg),
-                                                 T, D, Cn, ptr(loss), ptr(dx), ptr(dtable), ptr(dg), ptr(db), ptr(ws),
-                                                 stream_ptr(x.device)))
-        _lib.count_launches(8 if need_grad else 4)
+        with torch.cuda.device(x.device):
+            check(lib.grb_head_loss_forward_backward(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), ptr(tg),
+                                                     T, D, Cn, ptr(loss), ptr(dx), ptr(dtable), ptr(dg), ptr(db), ptr(ws),
+                                                     stream_ptr(x.device)))
         ctx.grads = (dx, dg, db, dtable)
         return loss
 
@@ -222,10 +290,16 @@ class HeadLossFn(torch.autograd.Function):
         dx, dg, db, dtable = ctx.grads
         ctx.grads = None
         if dx is None:
-            return (None,) * 8
+            return (None,) * 9
+        if ctx.direct:
+            with torch.cuda.device(dx.device):
+                check(_lib.load().grb_assert_unit_scalar(ptr(dloss.detach().float().contiguous()), stream_ptr(dx.device)))
+            return dx, None, None, None, None, None, None, None, None
         if ctx.sink is not None:
-            return dx, None, None, None, None, None, None, None
-        return dx * dloss, dg * dloss, db * dloss, dtable * dloss, None, None, None, None
+            sg, sb, st = ctx.sink
+            sg.add_(dg * dloss); sb.add_(db * dloss); st.addcmul_(dtable, dloss)
+            return dx * dloss, None, None, None, None, None, None, None, None
+        return dx * dloss, dg * dloss, db * dloss, dtable * dloss, None, None, None, None, None
 
 
 def head_logits(x, ln_g, ln_b, table, table_bf16, eps) -> torch.Tensor:
@@ -237,10 +311,46 @@ def head_logits(x, ln_g, ln_b, table, table_bf16, eps) -> torch.Tensor:
     xc = x.detach().contiguous().float()
     logits = torch.empty(B, L, Cn, dtype=torch.float32, device=x.device)
     ws = _u8(lib.grb_head_workspace_bytes(T, D, Cn), x.device)
-    check(lib.grb_head_logits(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), T, D, Cn, ptr(logits), ptr(ws),
-                              stream_ptr(x.device)))
-    _lib.count_launches(2)
+    with torch.cuda.device(x.device):
+        check(lib.grb_head_logits(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), T, D, Cn, ptr(logits), ptr(ws),
+                                  stream_ptr(x.device)))
     return logits
+
+
+# ------------------------------------------------------------------------------------------------ attention core alone
+def hstu_attention_fwd(P: torch.Tensor, meta: SeqMeta, H: int, pos_table: torch.Tensor, time_table: Optional[torch.Tensor],
+                       ntime: int = 64) -> torch.Tensor:
+    """P [B, L, 4D] bf16 = silu(x Wp^T + b) = [U | V | Q | K]  ->  O [B, L, D] bf16 (hstu.py:244-267); tcgen05 path."""
+    lib = _lib.load()
+    require_cuda(P)
+    B, L, D4 = P.shape
+    D = D4 // 4
+    has_time = time_table is not None and meta.timestamps is not None
+    dims = _dims(B, L, D, H, pos_table.shape[0], ntime if has_time else 0, 0.0, 0, None, 0)
+    O = torch.empty(B, L, D, dtype=torch.bfloat16, device=P.device)
+    seq = meta.struct()
+    with torch.cuda.device(P.device):
+        check(lib.grb_hstu_attention_forward(C.byref(dims), ptr(pos_table), ptr(time_table) if has_time else None, C.byref(seq), ptr(P), ptr(O),
+                                             stream_ptr(P.device)))
+    return O
+
+
+def hstu_attention_bwd(P, zp, dO, meta: SeqMeta, H: int, pos_table, time_table, ntime: int = 64):
+    """-> dzp [B, L, 4D] bf16 (columns V, Q, K written; U untouched = 0), dpos_table, dtime_table (fp32)."""
+    lib = _lib.load()
+    B, L, D4 = P.shape
+    D = D4 // 4
+    has_time = time_table is not None and meta.timestamps is not None
+    dims = _dims(B, L, D, H, pos_table.shape[0], ntime if has_time else 0, 0.0, 0, None, 0)
+    dzp = torch.zeros(B, L, D4, dtype=torch.bfloat16, device=P.device)
+    dpos = torch.zeros_like(pos_table, dtype=torch.float32)
+    dtime = torch.zeros_like(time_table, dtype=torch.float32) if has_time else None
+    scratch = _u8(lib.grb_hstu_attention_scratch_bytes(C.byref(dims)), P.device)
+    seq = meta.struct()
+    with torch.cuda.device(P.device):
+        check(lib.grb_hstu_attention_backward(C.byref(dims), ptr(pos_table), ptr(time_table) if has_time else None, C.byref(seq), ptr(P), ptr(zp),
+                                              ptr(dO), ptr(dzp), ptr(dpos), ptr(dtime), ptr(scratch), stream_ptr(P.device)))
+    return dzp, dpos, dtime
 
 
 # ------------------------------------------------------------------------------------------------ SASRec pieces
@@ -251,7 +361,6 @@ def layernorm_fwd(x, g, b, eps, want_bf16=True, want_f32=False):
     yf = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
     st = torch.empty(T, 2, dtype=torch.float32, device=x.device)
     check(lib.grb_layernorm_forward(ptr(x), ptr(g), ptr(b), float(eps), T, D, ptr(yb), ptr(yf), ptr(st), stream_ptr(x.device)))
-    _lib.count_launches(1)
     return yb, yf, st
 
 
@@ -262,7 +371,6 @@ def layernorm_bwd(dy, x, st, g, residual=None):
     dg = torch.zeros_like(g)
     db = torch.zeros_like(g)
     check(lib.grb_layernorm_backward(ptr(dy), ptr(x), ptr(st), ptr(g), ptr(residual), T, D, ptr(dx), ptr(dg), ptr(db), stream_ptr(x.device)))
-    _lib.count_launches(1)
     return dx, dg, db
 
 
@@ -275,7 +383,6 @@ def linear_fwd(xb, wb, bias, act, p=0.0, seed=0, seed_dev=None, site=0):
     a = torch.empty_like(z) if act else None
     check(lib.grb_linear_forward(ptr(xb), ptr(wb), ptr(bias), T, N, K, act, ptr(z), ptr(a), float(p), int(seed), ptr(seed_dev), site,
                                  stream_ptr(xb.device)))
-    _lib.count_launches(1)
     return z, a
 
 
@@ -286,7 +393,6 @@ def linear_residual_fwd(xb, wb, bias, residual, row_scale=None, p=0.0, seed=0, s
     y = torch.empty(*xb.shape[:-1], N, dtype=torch.float32, device=xb.device)
     check(lib.grb_linear_residual_forward(ptr(xb), ptr(wb), ptr(bias), ptr(residual), ptr(row_scale), T, N, K, ptr(y), float(p), int(seed),
                                           ptr(seed_dev), site, stream_ptr(xb.device)))
-    _lib.count_launches(1)
     return y
 
 
@@ -299,7 +405,6 @@ def linear_bwd(dyb, wb, xb, need_dx=True, dx_residual=None, need_dw=True):
     dw = torch.zeros(N, K, dtype=torch.float32, device=dyb.device) if need_dw else None
     db = torch.zeros(N, dtype=torch.float32, device=dyb.device) if need_dw else None
     check(lib.grb_linear_backward(ptr(dyb), ptr(wb), ptr(xb), T, N, K, ptr(dx), ptr(dx_residual), ptr(dw), ptr(db), stream_ptr(dyb.device)))
-    _lib.count_launches(3)
     return dx, dw, db
 
 
@@ -310,7 +415,6 @@ def sasrec_attention_fwd(q, k, v, pad, H, p=0.0, seed=0, seed_dev=None, layer=0)
     out = torch.empty_like(q)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=q.device)
     check(lib.grb_sasrec_attention_forward(C.byref(dims), ptr(q), ptr(k), ptr(v), ptr(pad), ptr(out), ptr(lse), stream_ptr(q.device)))
-    _lib.count_launches(1)
     return out, lse
 
 
@@ -321,7 +425,6 @@ def sasrec_attention_bwd(q, k, v, pad, out, lse, dout, H, p=0.0, seed=0, seed_de
     dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
     check(lib.grb_sasrec_attention_backward(C.byref(dims), ptr(q), ptr(k), ptr(v), ptr(pad), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk),
                                             ptr(dv), stream_ptr(q.device)))
-    _lib.count_launches(2)
     return dq, dk, dv
 
 
@@ -332,7 +435,6 @@ def linear_dact_bwd(dyb, wb, z, act, p=0.0, seed=0, seed_dev=None, site=0):
     g = torch.empty_like(z)
     check(_lib.load().grb_linear_dact_backward(ptr(dyb), ptr(wb), ptr(z), T, N, K, act, float(p), int(seed), ptr(seed_dev), site, ptr(g),
                                                stream_ptr(dyb.device)))
-    _lib.count_launches(1)
     return g
 
 
@@ -343,13 +445,11 @@ def cast_rows_bf16(x, row_scale=None, p=0.0, seed=0, seed_dev=None, site=0):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     check(_lib.load().grb_cast_rows_f32_to_bf16(ptr(x), ptr(out), T, D, ptr(row_scale), float(p), int(seed), ptr(seed_dev), site,
                                                 stream_ptr(x.device)))
-    _lib.count_launches(1)
     return out
 
 
 def dact_(g_bf16, z_bf16, act):
     check(_lib.load().grb_dact(ptr(g_bf16), ptr(z_bf16), g_bf16.numel(), act, stream_ptr(g_bf16.device)))
-    _lib.count_launches(1)
     return g_bf16
 
 
@@ -370,13 +470,13 @@ def rq_residual_argmin(x: torch.Tensor, codebooks: torch.Tensor, commitment: flo
     loss = torch.empty(N, dtype=torch.float32, device=x.device) if want_aux else None
     if N == 0:
         return ids, emb, res, loss
-    check(lib.grb_rq_residual_argmin(ptr(x), ptr(cb), N, D, K, levels, float(commitment), ptr(ids), ptr(emb), ptr(res), ptr(loss), None,
-                                     stream_ptr(x.device)))
-    _lib.count_launches(1)
+    with torch.cuda.device(x.device):
+        check(lib.grb_rq_residual_argmin(ptr(x), ptr(cb), N, D, K, levels, float(commitment), ptr(ids), ptr(emb), ptr(res), ptr(loss), None,
+                                         stream_ptr(x.device)))
     return ids, emb, res, loss
 
 
 def adam_step(p, g, m, v, p_bf16, state, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, zero_grad=True):
-    check(_lib.load().grb_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), ptr(state), lr, beta1, beta2, eps, weight_decay,
-                                    grad_scale, int(zero_grad), stream_ptr(p.device)))
-    _lib.count_launches(2)
+    with torch.cuda.device(p.device):
+        check(_lib.load().grb_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), ptr(state), lr, beta1, beta2, eps, weight_decay,
+                                        grad_scale, int(zero_grad), stream_ptr(p.device)))

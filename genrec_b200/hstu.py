@@ -229,6 +229,7 @@ class HSTU(nn.Module):
         self._table_bf16 = None
         self._bf16_provider = None
         self._grad_sink = None
+        self._unit_loss_grad = False   # FlatAdam(unit_loss_grad=True): head gradients go straight into the flat buffer (see HeadLossFn)
         self._step_seed = 0
         self._seed_dev = None  # device uint64 counter, bumped once per training forward (CUDA-graph-safe dropout reseeding)
         self._init_weights()
@@ -268,7 +269,9 @@ class HSTU(nn.Module):
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
             self._step_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         self._seed_dev.add_(0x9E3779B1)  # captured by CUDA graphs: every replay draws fresh masks
-        return self._step_seed, self._seed_dev
+        # per-forward snapshot: the backward re-derives the masks from the value THIS forward saw, even when another
+        # training-mode forward has bumped the counter in between
+        return self._step_seed, self._seed_dev.clone()
 
     def encode(self, input_ids: torch.Tensor, timestamps: Optional[torch.Tensor]) -> torch.Tensor:
         """Embedding + all blocks (everything before final_norm).  hstu.py:117-132."""
@@ -306,7 +309,7 @@ class HSTU(nn.Module):
             if self._grad_sink is not None and torch.is_grad_enabled():
                 hsink = (self._grad_sink(self.final_norm.weight), self._grad_sink(self.final_norm.bias), self._grad_sink(table))
             loss = Fn.HeadLossFn.apply(x, self.final_norm.weight, self.final_norm.bias, table, table_bf16, targets,
-                                       self.final_norm.eps, hsink)
+                                       self.final_norm.eps, hsink, self._unit_loss_grad)
         if targets is None or not self.training or self.return_train_logits:
             logits = Fn.head_logits(x, self.final_norm.weight, self.final_norm.bias, table, table_bf16, self.final_norm.eps)
         return logits, loss

@@ -69,7 +69,11 @@ def allreduce_gradients(buffers: FlatBuffers, group=None) -> float:
 
 class FlatAdam:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True):
+                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True, unit_loss_grad: bool = False):
+        """``unit_loss_grad=True`` promises that every training forward is followed by exactly one ``loss.backward()`` with
+        gradient 1 (no loss scaling, no gradient accumulation through a scaled loss): the fused head then accumulates its
+        parameter gradients into the flat buffer in the same pass that computes the loss.  The promise is checked on the
+        device (``grb_assert_unit_scalar``).  Default False: fully general, a few microseconds slower per step."""
         self.buffers = FlatBuffers(model)
         dev = self.buffers.device
         assert dev.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
@@ -87,6 +91,11 @@ class FlatAdam:
                 mod._bf16_provider = self.buffers.mirror_of
             if grad_sink and hasattr(mod, "_grad_sink"):
                 mod._grad_sink = self.buffers.grad_of
+            if grad_sink and hasattr(mod, "_unit_loss_grad"):
+                mod._unit_loss_grad = bool(unit_loss_grad)
+        # the kernels read the bf16 mirror, never the fp32 masters: anything that rewrites the masters behind the optimizer's
+        # back (load_state_dict on resume, accelerate.load_state) must refresh it
+        self._hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_mirror())
 
     def mirror_of(self, p: torch.Tensor) -> torch.Tensor:
         return self.buffers.mirror_of(p)
@@ -105,3 +114,22 @@ class FlatAdam:
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         pass  # the fused step already zeroed the flat gradient
+
+    def refresh_mirror(self) -> None:
+        """Re-derive the bf16 operand mirror from the fp32 masters.  Called automatically after ``model.load_state_dict``;
+        call it yourself after editing ``param.data`` in place (manual re-initialisation)."""
+        Fn.cast_bf16(self.flat, self.mirror)
+
+    def state_dict(self) -> dict:
+        """Adam moments + step state (``torch.optim.Adam``-style checkpointing; parameters live in ``model.state_dict()``)."""
+        return {"m": self.m.clone(), "v": self.v.clone(), "state": self.state.clone(),
+                "hyper": dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay), "n": self.n}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if int(sd["n"]) != self.n:
+            raise ValueError(f"FlatAdam state for {sd['n']} elements does not fit this model ({self.n})")
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.state.copy_(sd["state"])
+        h = sd.get("hyper", {})
+        self.lr, self.betas = h.get("lr", self.lr), tuple(h.get("betas", self.betas))
+        self.eps, self.weight_decay = h.get("eps", self.eps), h.get("weight_decay", self.weight_decay)
+        self.refresh_mirror()

@@ -199,7 +199,8 @@ class SASRec(nn.Module):
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
             self._step_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         self._seed_dev.add_(0x9E3779B1)
-        return self._step_seed, self._seed_dev
+        # per-forward snapshot: the backward re-derives the masks from the value THIS forward saw
+        return self._step_seed, self._seed_dev.clone()
 
     def forward(self, input_ids: torch.Tensor, targets: Optional[torch.Tensor] = None
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:

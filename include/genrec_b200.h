@@ -71,14 +71,37 @@ typedef struct {             /* fp32, same shapes as the parameters, accumulated
 } grb_hstu_layer_grads;
 
 typedef struct {
-    const uint16_t* bias_index; /* [B, L, ld_index] from grb_hstu_bias_index(): pos_bucket(i-j)*64 + time_bucket(|ts_i-ts_j|),
-                                   or npos*64 for a masked cell (j > i, padded key) */
+    const uint16_t* bias_index; /* LEGACY (mma.sync) attention path only, NULL otherwise: [B, L, ld_index] from grb_hstu_bias_index():
+                                   pos_bucket(i-j)*64 + time_bucket(|ts_i-ts_j|), or npos*64 for a masked cell (j > i, padded key) */
     int ld_index;               /* row pitch in ELEMENTS: a multiple of 8, >= L */
     int has_time;               /* 0: timestamps were None -> the temporal term is dropped (hstu.py:251) */
     int pos_uniform;            /* 1 when every delta in [0, L) maps to the same position bucket (the reference's behaviour):
-                                   bias_index must then have been built with npos = 1 and an all-zero pos_bucket table */
+                                   a bias_index, if given, must then have been built with npos = 1 and an all-zero pos_bucket table */
     int pos_bucket0;            /* that bucket (row of the [npos, H] table that is live) */
+    /* tcgen05 attention path (the default): buckets and masks are derived inside the attention kernels from these */
+    const int64_t* timestamps;  /* [B, L] or NULL */
+    const uint8_t* pad;         /* [B, L], 1 = input_ids == 0 */
+    const int32_t* rel32;       /* [B, L] from grb_hstu_seq_prepare() (NULL when timestamps is NULL) */
+    const uint8_t* wide;        /* [B]    from grb_hstu_seq_prepare() */
+    const int64_t* time_thr;    /* [65] integer thresholds of the reference's fp32 log/0.693 bucket expression (see below) */
 } grb_hstu_seq;
+
+/* Per-sequence rebasing of the int64 timestamps (replaces nothing in the reference: it makes `ts[b,i] - ts[b,j]`
+ * (hstu.py:400) a 32-bit subtraction inside the attention kernels): rel32[b,i] = ts[b,i] - min over non-padded positions;
+ * wide[b] = 1 when the sequence spans >= 2^31 ticks, in which case the kernels use the int64 values themselves. */
+int grb_hstu_seq_prepare(const int64_t* timestamps, const uint8_t* pad, int B, int L, int32_t* rel32, uint8_t* wide, void* stream);
+/* Test hook: the time bucket / mask byte the tcgen05 attention kernels derive for every cell, [B, L, L] uint8
+ * (bucket, or 64 when j > i or key j is padded), computed by the very device routine the kernels use. */
+int grb_hstu_bucket_bytes_debug(const grb_hstu_seq* s, int B, int L, int ntime, uint8_t* out, void* stream);
+/* The attention core alone (hstu.py:244-267) on the projection output P = [U | V | Q | K] ([T, 4D] bf16): O [T, D] bf16.
+ * backward: dO [T, D] bf16, zp [T, 4D] the pre-activations of P -> dzp columns V, Q, K (gradients w.r.t. the pre-activations),
+ * bias-table gradients accumulated.  scratch: grb_hstu_attention_scratch_bytes(). */
+size_t grb_hstu_attention_scratch_bytes(const grb_hstu_dims* d);
+int grb_hstu_attention_forward(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s,
+                               const void* P_bf16, void* O_bf16, void* stream);
+int grb_hstu_attention_backward(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s,
+                                const void* P_bf16, const void* zp_bf16, const void* dO_bf16, void* dzp_bf16, float* dpos_table,
+                                float* dtime_table, void* scratch, void* stream);
 
 /* Per-batch integer preprocessing shared by all layers / heads / passes (replaces the index arithmetic of
  * RelativePositionBias._relative_position_bucket (hstu.py:300-328), TemporalBias._temporal_bucket (:368-384) and the two
@@ -162,6 +185,11 @@ int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream
 /* torch.optim.Adam semantics on a flat buffer; state = 3 floats {step, 1-b1^step, 1-b2^step} ticked ON DEVICE. */
 int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n, float* state, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, void* stream);
+
+/* Device-side contract check: traps (asynchronous CUDA error at the next synchronisation) unless *value == 1.0f.  Used by the
+ * opt-in "unit loss gradient" fast path, where parameter gradients are accumulated into the flat buffer before the incoming
+ * gradient of the loss is known. */
+int grb_assert_unit_scalar(const float* value, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ RQ-VAE residual argmin
  * Replaces the Quantize.forward distance+argmin (genrec/models/rqvae.py:185-199, eval branch :246-248) iterated by
