@@ -29,7 +29,14 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-CFG = dict(num_items=12101, max_seq_len=200, embed_dim=128, num_heads=4, num_blocks=4, dropout=0.2)
+CONFIGS = {
+    # BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[2] (the long-sequence regime)
+    "cfg2": dict(model=dict(num_items=12101, max_seq_len=200, embed_dim=128, num_heads=4, num_blocks=4, dropout=0.2), batch=128,
+                 cpu_batch=32, eager_batch=128),
+    "cfg3": dict(model=dict(num_items=12101, max_seq_len=2048, embed_dim=256, num_heads=8, num_blocks=8, dropout=0.2), batch=32,
+                 cpu_batch=1, eager_batch=4),
+}
+CFG = dict(CONFIGS["cfg2"]["model"])
 METRIC = "hstu_train_sequences_per_sec"
 UNIT = "sequences/s"
 
@@ -39,15 +46,25 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="sequences per GPU")
-    ap.add_argument("--seq-len", type=int, default=CFG["max_seq_len"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cuda_eager"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="cfg2 = BASELINE configs[1] (default), cfg3 = configs[2]")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU")
+    ap.add_argument("--seq-len", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a captured CUDA graph")
-    ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--cpu-batch", type=int, default=None)
+    ap.add_argument("--eager-batch", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    c = CONFIGS[args.config]
+    CFG.clear(); CFG.update(c["model"])
+    args.batch = args.batch or c["batch"]
+    args.seq_len = args.seq_len or CFG["max_seq_len"]
+    args.cpu_batch = args.cpu_batch or c["cpu_batch"]
+    args.eager_batch = args.eager_batch or c["eager_batch"]
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
@@ -123,7 +140,8 @@ def usable_cpus() -> int:
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_arm(batch, L, seconds, steps=None, warmup=1):
     """The reference's CPU-eager algorithm (oracle restatement, fp32, all host threads), full train-step fwd+bwd
-    (+ Adam) on a bounded sample of the same workload.  The ONLY place bench.py executes oracle/."""
+    (+ Adam) on a bounded sample of the same workload.  bench.py executes oracle/ only in its baseline legs (this one,
+    --impl reference, and the same-GPU eager arm)."""
     from oracle import hstu as oh
     from genrec_b200.hstu import HSTU
     threads = usable_cpus()
@@ -155,6 +173,55 @@ def cpu_arm(batch, L, seconds, steps=None, warmup=1):
                 ms_per_step=1e3 * sum(times) / len(times))
 
 
+def cuda_eager_arm(batch, L, dev, steps, warmup=2):
+    """The reference's algorithm as plain PyTorch eager ON THE SAME GPU (oracle restatement, torch.autocast(bf16), dropout 0, Adam):
+    the "beat this on the same box" number of BASELINE.md section 2.2 - the reference ships no kernel of its own."""
+    from oracle import hstu as oh
+    from genrec_b200.hstu import HSTU
+    torch.manual_seed(0)
+    m = HSTU(**{**CFG, "max_seq_len": L, "dropout": 0.0})
+    params = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3, betas=(0.9, 0.98))
+    ids, ts, tg = (t.to(dev) for t in synth_batch(batch, L, CFG["num_items"], 123))
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, loss = oh.hstu_forward(ids, ts, tg, params, CFG["num_heads"], CFG["num_blocks"])
+        loss.float().backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(batch=batch, ms_per_step=ms, seq_per_s=batch / (ms * 1e-3), loss=float(loss))
+
+
+def run_cuda_eager(args, rank, world, local_rank):
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = args.seq_len
+    r = cuda_eager_arm(args.eager_batch, L, dev, max(1, args.steps), max(2, min(args.warmup, 3)))
+    line = dict(impl="cuda_eager", metric=METRIC, value=r["seq_per_s"], unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 autocast", data="synthetic",
+                config=dict(workload=workload_name(L) + " - reference algorithm, PyTorch eager on cuda:0", batch_per_step=args.eager_batch))
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(L):
+    return (f"HSTU {CFG['num_blocks']} blocks d={CFG['embed_dim']} h={CFG['num_heads']} seq_len={L} V={CFG['num_items']}")
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; /root/reference does not travel
     to the GPU box), all host threads, same config/metric; rank 0 only."""
@@ -162,8 +229,10 @@ def run_reference(args, rank, world):
         return
     L = args.seq_len
     r = cpu_arm(args.cpu_batch, L, seconds=0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-    cfg = dict(workload=f"HSTU {CFG['num_blocks']}L d={CFG['embed_dim']} h={CFG['num_heads']} seq_len={L} V={CFG['num_items']} "
-                        f"train step (fwd+bwd+Adam), CPU-eager fp32", batch_per_step=args.cpu_batch)
+    cfg = dict(workload=workload_name(L) + " train step (fwd+bwd+Adam), CPU-eager fp32", batch_per_step=args.cpu_batch,
+               same_config=False,
+               mismatch=f"CPU arm: B={args.cpu_batch} per step, fp32, dropout 0, oracle port of the reference modules; "
+                        f"GPU arm: B={args.batch} per GPU, bf16 operands, dropout {CFG['dropout']}")
     line = dict(impl="reference", metric=METRIC, value=r["seq_per_s"], unit=UNIT, n_gpus=args.gpus, steps=len(r["times"]),
                 warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", config=cfg,
@@ -187,7 +256,8 @@ def run_ours(args, rank, world, local_rank):
     K, W = args.steps, max(args.warmup, 3)
     torch.manual_seed(0)  # identical init on every rank (DDP broadcast equivalent)
     model = HSTU(**{**CFG, "max_seq_len": L}).to(dev).train()
-    opt = FlatAdam(model, lr=1e-3, betas=(0.9, 0.98))
+    # plain loss.backward() every step: the head may accumulate straight into the flat gradient buffer (checked on the device)
+    opt = FlatAdam(model, lr=1e-3, betas=(0.9, 0.98), unit_loss_grad=True)
 
     nb = 8
     host = [tuple(t.pin_memory() for t in synth_batch(B, L, V, 1000 * rank + i)) for i in range(nb)]
@@ -257,22 +327,27 @@ def run_ours(args, rank, world, local_rank):
                 torch.cuda.current_stream().synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         t0 = time.perf_counter()
         e0.record()
+        marks[0].record()
         for i in range(K):
             loader(W + i)
             run_step()
             if sync_each:
                 loss_host.copy_(loss_static.detach(), non_blocking=True)
                 torch.cuda.current_stream().synchronize()   # the trainer's per-step loss.item() (hstu_trainer.py:163)
+            marks[i + 1].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
         wall = (time.perf_counter() - t0) * 1e3
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
+        pct = dict(p10=per[int(0.1 * (K - 1))], p50=per[K // 2], p90=per[int(0.9 * (K - 1) + 0.5)])
         t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item(), t[1].item()
+        return t[0].item(), t[1].item(), pct
 
     try:
         gpu_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
@@ -281,9 +356,9 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(gpu_index)
     if rank == 0:
         sampler.start()
-    ms_dev, _ = timed(load_resident, sync_each=False)
+    ms_dev, _, pct_dev = timed(load_resident, sync_each=False)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, wall_e2e = timed(load_host, sync_each=True)
+    ms_e2e, wall_e2e, pct_e2e = timed(load_host, sync_each=True)
     final_loss = float(loss_static.detach().float().item())
 
     # ---- roofline of the HSTU block stack (fwd+bwd), device-timed inside a graph
@@ -295,26 +370,43 @@ def run_ours(args, rank, world, local_rank):
         try:
             r = cpu_arm(args.cpu_batch, L, args.cpu_seconds)
             cpu = dict(value=r["seq_per_s"], unit=UNIT, cores=r["threads"], kind="port",
-                       sample=f"{len(r['times'])} train steps of B={args.cpu_batch} x L={L} (oracle port of the reference CPU-eager path, fp32)")
+                       sample=f"{len(r['times'])} train steps of B={args.cpu_batch} x L={L} (oracle port of the reference CPU-eager path, fp32)",
+                       same_config=False, mismatch=f"B={args.cpu_batch} per step, fp32, dropout 0 (GPU arm: B={B}, bf16, dropout {CFG['dropout']})")
         except Exception as e:  # noqa: BLE001
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
+    used_graph = graph is not None
+    eager = None
+    if rank == 0 and not args.skip_eager:
+        used_graph = graph is not None
+        graph = None
+        torch.cuda.empty_cache()
+        try:
+            r = cuda_eager_arm(args.eager_batch, L, dev, steps=5 if args.config == "cfg2" else 2)
+            eager = dict(value=r["seq_per_s"], unit=UNIT, ms_per_step=r["ms_per_step"], batch=r["batch"],
+                         what="the reference's algorithm as PyTorch eager + autocast(bf16) on this same GPU (oracle restatement, dropout 0, Adam)")
+        except Exception as e:  # noqa: BLE001
+            eager = dict(value=None, unit=UNIT, what=f"failed: {type(e).__name__}: {e}")
     if rank != 0:
         return
     gb = B * world
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     line = dict(metric=METRIC, value=gb * K / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_dev / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=f"HSTU {CFG['num_blocks']} blocks d={CFG['embed_dim']} h={CFG['num_heads']} seq_len={L} "
-                                     f"V={V} dropout={CFG['dropout']} full train step (emb, blocks, tied logits+CE, bwd, "
-                                     f"{'all-reduce, ' if world > 1 else ''}Adam)",
+                config=dict(workload=workload_name(L) + f" dropout={CFG['dropout']} full train step (emb, blocks, tied logits+CE, bwd, "
+                                     f"{'all-reduce, ' if world > 1 else ''}Adam)", name=args.config,
                             global_batch=gb, batch_per_gpu=B, seq_len=L, parallelism=f"dp{world}",
-                            cuda_graph=graph is not None,
-                            l2="per-step working set (activations + logits, ~1.5 GB) exceeds the 126 MB L2; no explicit flush",
-                            final_loss=final_loss),
+                            cuda_graph=used_graph,
+                            l2="per-step working set (activations + logits, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+                            final_loss=final_loss, ms_per_step_pct=pct_dev),
                 e2e=dict(value=gb * K / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                         ms_per_step=ms_e2e / K, wall_ms_per_step=wall_e2e / K),
-                gpu_launches=launches_per_step * K, clocks=clocks, roofline=roof, cpu_baseline=cpu)
+                         ms_per_step=ms_e2e / K, wall_ms_per_step=wall_e2e / K, ms_per_step_pct=pct_e2e),
+                gpu_launches=launches_per_step * K, clocks=clocks, roofline=roof, cpu_baseline=cpu, cuda_eager_baseline=eager)
     print(json.dumps(line), flush=True)
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the block stack's kernels for one fwd+bwd, from the committed ncu
+# capture of the same command (profiles/*_step_dram_traffic.txt, scripts/step_traffic.py); keyed by (B, L, D, layers)
+TRAFFIC_NCU = {(128, 200, 128, 4): 2.106e9}
 
 
 def block_roofline(model, B, L, dev, K):
@@ -370,7 +462,7 @@ def block_roofline(model, B, L, dev, K):
     ach = flops / (ms * 1e-3) / 1e12
     # DRAM bytes (read + write) of the block stack's kernels for one fwd+bwd at the default geometry, summed from the ncu
     # capture profiles/r1_step_dram_traffic.txt (scripts/step_traffic.py); not re-measured here (needs a profiler)
-    traffic = 2.106e9 if (B, L, D, nl) == (128, 200, 128, 4) else None
+    traffic = TRAFFIC_NCU.get((B, L, D, nl))
     return dict(bound="tensor", kernel="hstu_block_stack_fwd_bwd", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                 peak_source=which, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 algorithmic_bytes_per_launch=(10 * L * D + 9 * L) * B * nl, ms_per_launch=ms, flops_per_launch=flops,
@@ -385,11 +477,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.impl == "cuda_eager":
+        run_cuda_eager(args, rank, world, local_rank)
+        return
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the single JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)

@@ -40,14 +40,14 @@ def position_bucket(rel: torch.Tensor, num_buckets: int = 32, max_distance: int 
     return torch.where(small, rel, large)                        # hstu.py:327
 
 
-def position_bias(table: torch.Tensor, L: int, num_buckets: int = 32, max_distance: int = 128) -> torch.Tensor:
+def position_bias(table: torch.Tensor, L: int, num_buckets: int = 32, max_distance: int = 128) -> torch.Tensor:  # noqa: E302
     """[H, L, L] bias.  Follows genrec/models/hstu.py:330-349.
 
     NOTE the reference builds ``pos[None,:] - pos[:,None]`` = (j - i) for cell
     (i, j) (hstu.py:340) - the opposite sign of its comment - then clamps at 0,
     so every causal cell (j <= i) lands in bucket 0.
     """
-    pos = torch.arange(L)
+    pos = torch.arange(L, device=table.device)
     rel = pos.unsqueeze(0) - pos.unsqueeze(1)                    # [i, j] = j - i
     bkt = position_bucket(rel, num_buckets, max_distance)
     return table[bkt].permute(2, 0, 1)                           # [H, L, L]
@@ -96,7 +96,7 @@ def hstu_layer_forward(
     if use_temporal_bias and timestamps is not None:                              # :251
         S = S + temporal_bias(g("temporal_bias.temporal_attention_bias.weight"), timestamps)
 
-    causal = torch.triu(torch.ones(L, L), diagonal=1).bool()                     # hstu.py:121
+    causal = torch.triu(torch.ones(L, L, device=x.device), diagonal=1).bool()    # hstu.py:121
     S = S.masked_fill(causal[None, None], -1e9)                                   # :256
     S = S.masked_fill(padding_mask[:, None, None, :], -1e9)                       # :259
     A = F.silu(S)                                                                 # :263
