@@ -71,6 +71,7 @@ SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "grb_head_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p]),
+    "grb_eval_rank_metrics": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "grb_sasrec_attention_forward": (c_int, [P(SasrecDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p]),
     "grb_sasrec_attention_backward": (c_int, [P(SasrecDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -89,6 +90,8 @@ SIGNATURES = {
                                       c_void_p]),
     "grb_layernorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p, c_void_p]),
+    "grb_split3_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "grb_linear_f32x3_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "grb_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "grb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,
                               c_float, c_float, c_float, c_float, c_int, c_void_p]),

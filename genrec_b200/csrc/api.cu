@@ -809,6 +809,15 @@ int grb_head_logits(const float* x, const float* ln_g, const float* ln_b, float 
     return 0;
 }
 
+int grb_eval_rank_metrics(const float* logits, const int64_t* targets, int B, int C, float* metrics, int32_t* ranks, void* stream) {
+    GRB_REQUIRE(logits && targets && metrics, "null argument");
+    GRB_REQUIRE(B > 0 && C > 1, "bad shape B=%d C=%d", B, C);
+    launch_k(eval_rank_kernel, (unsigned)B, 256, 0, static_cast<cudaStream_t>(stream), logits, C, reinterpret_cast<const long long*>(targets), metrics,
+             reinterpret_cast<int*>(ranks));
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ SASRec attention
 namespace {
 int sas_args(const grb_sasrec_dims* d, SasAttnArgs& a) {
@@ -960,6 +969,28 @@ int grb_layernorm_backward(const float* dy, const float* x, const float* stats, 
     return 0;
 }
 
+int grb_split3_f32_to_bf16(const float* in, void* out_bf16, size_t rows, int K, int operand, void* stream) {
+    GRB_REQUIRE(in && out_bf16 && K > 0 && (operand == 0 || operand == 1), "bad argument");
+    if (rows == 0) return 0;
+    size_t blocks = (rows * (size_t)K + 255) / 256;
+    if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+    launch_k(split3_f32_bf16_kernel, (unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream), in, (bf16*)out_bf16, rows, K, operand);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16, int T, int N, int K, int act, float* y, void* stream) {
+    GRB_REQUIRE(x_split_bf16 && w_split_bf16 && y, "null argument");
+    GRB_REQUIRE(T > 0 && N % 4 == 0 && K % 8 == 0 && (act == 0 || act == 1), "bad shape T=%d N=%d K=%d act=%d", T, N, K, act);
+    GRB_REQUIRE(aligned16(x_split_bf16) && aligned16(w_split_bf16) && aligned16(y), "buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K6 = 6 * K;
+    if (act == 1)
+        GRB_CUDA((launch_tc_gemm<0, 0>((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, T, N, K6, K6, K6, 1, TcEpiActF32<1>{}, y, nullptr, N, sm_count(), st)));
+    else
+        GRB_CUDA((launch_tc_gemm<0, 0>((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, T, N, K6, K6, K6, 1, TcEpiActF32<0>{}, y, nullptr, N, sm_count(), st)));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ optimizer / casts
 int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream) {
     GRB_REQUIRE(in && out_bf16, "null argument");
@@ -1011,8 +1042,33 @@ int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, in
     GRB_REQUIRE(aligned16(x) && aligned16(codebooks), "buffers must be 16-byte aligned");
     if (N == 0) return 0;
     RqArgs a{x, codebooks, reinterpret_cast<long long*>(ids), emb, res, loss, res_out, (long long)N, K, levels, commitment};
-    size_t smem = (size_t)K * (D + 1) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GRB_REQUIRE(emb == nullptr || aligned16(emb), "emb must be 16-byte aligned");
+    GRB_REQUIRE(res == nullptr || aligned16(res), "res must be 16-byte aligned");
+    const bool legacy = getenv("GRB_RQ") != nullptr && strcmp(getenv("GRB_RQ"), "thread") == 0;   // one-thread-per-row first generation
+    if (!legacy && K % 8 == 0) {
+        // four threads per row (see rq_argmin.cuh); two rows per thread once there is more than a wave of work (FMA : LDS = 8 : 1)
+        const int rows = (D == 32 && N > (int64_t)sm_count() * RQ_ROWS_PER_CTA * 4) ? 2 : 1;
+        const size_t base = ((size_t)K * D + ((K + 3) & ~3)) * sizeof(float);
+        const size_t stage = (emb || res) ? (size_t)2 * RQ_ROWS_PER_CTA * rows * D * levels * sizeof(float) : 0;
+        const bool staged = stage > 0 && base + stage <= 200 * 1024;
+        const size_t smem = base + (staged ? stage : 0);
+        const unsigned grid = (unsigned)((N + (int64_t)RQ_ROWS_PER_CTA * rows - 1) / ((int64_t)RQ_ROWS_PER_CTA * rows));
+        auto go = [&](auto kern) -> int {
+            GRB_TRY(set_smem(kern, smem));
+            launch_k(kern, grid, RQ_THREADS, smem, st, a);
+            return 0;
+        };
+        if (D == 32) {
+            if (rows == 2) GRB_TRY(staged ? go(rq_residual_argmin_split_kernel<32, 2, true>) : go(rq_residual_argmin_split_kernel<32, 2, false>));
+            else GRB_TRY(staged ? go(rq_residual_argmin_split_kernel<32, 1, true>) : go(rq_residual_argmin_split_kernel<32, 1, false>));
+        } else {
+            GRB_TRY(staged ? go(rq_residual_argmin_split_kernel<64, 1, true>) : go(rq_residual_argmin_split_kernel<64, 1, false>));
+        }
+        GRB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    size_t smem = (size_t)K * (D + 1) * sizeof(float);
     if (D == 32) {
         // two rows per thread once there is more than a wave of work; one row per thread for small N (more CTAs)
         if (N > (int64_t)sm_count() * RQ_THREADS * 2) {

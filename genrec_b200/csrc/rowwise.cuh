@@ -713,4 +713,66 @@ __global__ void cast_flat_f32_bf16_kernel(const float* __restrict__ in, bf16* __
     for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
 }
 
+
+// ------------------------------------------------------------------------------------------------ split-bf16 operands
+// fp32-accurate GEMM on the bf16 tensor path: x = hi + mid + lo with three bf16 terms (24 mantissa bits together); the product
+// of two such numbers keeps the six terms of weight >= 2^-16 (hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid).  Laying the terms
+// out along K,   A' = [hi | hi | mid | hi | lo | mid]   B' = [hi | mid | hi | lo | hi | mid]   (K' = 6 K),
+// turns the sum of the six partial GEMMs into ONE ordinary GEMM with fp32 accumulation in TMEM.
+// out [rows, 6 K] bf16 ; operand 0 = A layout, 1 = B layout.
+__global__ void __launch_bounds__(256) split3_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t rows, int K, int operand) {
+    pdl_wait();
+    const size_t n = rows * (size_t)K;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / K;
+        const int k = (int)(e % K);
+        const float x = in[e];
+        const bf16 hi = __float2bfloat16_rn(x);
+        const float r1 = x - __bfloat162float(hi);
+        const bf16 mid = __float2bfloat16_rn(r1);
+        const bf16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        bf16* o = out + r * (size_t)(6 * K) + k;
+        if (operand == 0) { o[0] = hi; o[K] = hi; o[2 * K] = mid; o[3 * K] = hi; o[4 * K] = lo; o[5 * K] = mid; }
+        else              { o[0] = hi; o[K] = mid; o[2 * K] = hi; o[3 * K] = lo; o[4 * K] = hi; o[5 * K] = mid; }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ leave-one-out metrics
+// Replaces the per-sample Python loop of genrec/trainers/hstu_trainer.py:55-81 (`logits[:, 0] = -inf`, top-k, `.item()` per
+// sample): the rank of the held-out target among classes 1..C-1 is counted directly - rank = 1 + #{j >= 1 : logit_j > logit_t or
+// (logit_j == logit_t and j < t)} (torch.topk's order on ties: lower index first) - and Recall@k / NDCG@k for k in {1, 5, 10}
+// are ACCUMULATED on the device:  out[0..2] += hit@{1,5,10}, out[3..5] += ndcg@{1,5,10}.  One CTA per sample; targets of 0
+// (padding) contribute nothing.  ranks (nullable) receives the per-sample rank (0 for skipped samples).
+__global__ void __launch_bounds__(256) eval_rank_kernel(const float* __restrict__ logits, int C, const long long* __restrict__ targets,
+                                                       float* __restrict__ out, int* __restrict__ ranks) {
+    pdl_wait();
+    __shared__ int red[8];
+    const int b = blockIdx.x;
+    const long long t = targets[b];
+    if (t <= 0 || t >= C) {
+        if (threadIdx.x == 0 && ranks) ranks[b] = 0;
+        return;
+    }
+    const float* row = logits + (size_t)b * C;
+    const float lt = row[t];
+    int c = 0;
+    for (int j = 1 + threadIdx.x; j < C; j += 256) {
+        const float v = row[j];
+        c += (v > lt) || (v == lt && j < (int)t);
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int rank = 1;
+        for (int w = 0; w < 8; ++w) rank += red[w];
+        if (ranks) ranks[b] = rank;
+        const float nd = 1.f / log2f((float)rank + 1.f);
+        if (rank <= 1) { atomicAdd(out + 0, 1.f); atomicAdd(out + 3, nd); }
+        if (rank <= 5) { atomicAdd(out + 1, 1.f); atomicAdd(out + 4, nd); }
+        if (rank <= 10) { atomicAdd(out + 2, 1.f); atomicAdd(out + 5, nd); }
+    }
+}
+
 }  // namespace grb

@@ -137,4 +137,178 @@ __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_kernel(RqArgs a
     }
 }
 
+// ------------------------------------------------------------------------------------------------ split variant
+// The same arithmetic (dot products accumulated in the same order, the same (|r|^2 + |c|^2) - 2 r.c expression, strict '<' on
+// an ascending code index), but a row is scanned by FOUR threads, each walking a quarter of the codes; the quarters meet
+// through two shuffles (lower index wins ties, so the first-index rule of torch.min survives).  N = 12,101 items become 189
+// CTAs instead of 48, and a row's serial chain is 64 codes instead of 256.  Lanes are laid out quarter-major (lane = q * 8 +
+// row): the 8 lanes of a shared-memory phase read ONE code word (a broadcast), so the LDS.128 stays conflict-free.
+// Optional outputs in the reference's [N, D, levels] layout are staged in shared memory per row and written once, as whole
+// contiguous rows with 16-byte stores (writing them level by level is a stride-`levels` scatter at ~5 % of HBM speed).
+constexpr int RQ_SPLIT = 4;
+constexpr int RQ_ROWS_PER_CTA = RQ_THREADS / RQ_SPLIT;   // x ROWS
+
+template <int D, int ROWS, bool STAGE>
+__global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_split_kernel(RqArgs a) {
+    pdl_wait();
+    extern __shared__ __align__(16) float rq_smem[];
+    float* cb = rq_smem;             // [K][D]
+    float* cn = rq_smem + a.K * D;   // [K] squared norms
+    float* st_emb = cn + ((a.K + 3) & ~3);                                   // [rows of the CTA][D * levels]   (STAGE)
+    float* st_res = st_emb + (size_t)RQ_ROWS_PER_CTA * ROWS * D * a.levels;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = lane >> 3;                         // code quarter
+    const int rl = warp * 8 + (lane & 7);            // row slot inside the CTA (0 .. 63), x ROWS
+    const int kq = a.K / RQ_SPLIT;                   // codes per quarter (K % 8 == 0 checked by the host)
+    const long long row0 = (long long)blockIdx.x * RQ_ROWS_PER_CTA * ROWS;
+    long long row[ROWS];
+    bool live[ROWS];
+    float r[ROWS][D];
+#pragma unroll
+    for (int w = 0; w < ROWS; ++w) {
+        row[w] = row0 + (long long)w * RQ_ROWS_PER_CTA + rl;
+        live[w] = row[w] < a.N;
+        if (live[w]) {
+#pragma unroll
+            for (int j = 0; j < D; j += 4) {
+                float4 v = *reinterpret_cast<const float4*>(a.x + row[w] * D + j);
+                r[w][j] = v.x; r[w][j + 1] = v.y; r[w][j + 2] = v.z; r[w][j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) r[w][j] = 0.f;
+        }
+    }
+    float loss[ROWS];
+#pragma unroll
+    for (int w = 0; w < ROWS; ++w) loss[w] = 0.f;
+    constexpr int JQ = D / RQ_SPLIT;   // columns of a row each of its four threads writes out
+
+    for (int l = 0; l < a.levels; ++l) {
+        __syncthreads();
+        const float* g = a.codebooks + (size_t)l * a.K * D;
+        for (int i = tid * 4; i < a.K * D; i += RQ_THREADS * 4)
+            *reinterpret_cast<float4*>(cb + i) = *reinterpret_cast<const float4*>(g + i);
+        __syncthreads();
+        for (int k = tid; k < a.K; k += RQ_THREADS) {
+            float s = 0.f;
+            for (int j = 0; j < D; ++j) s = fmaf(cb[k * D + j], cb[k * D + j], s);
+            cn[k] = s;
+        }
+        __syncthreads();
+
+        float xn[ROWS], best[ROWS];
+        int best_k[ROWS];
+#pragma unroll
+        for (int w = 0; w < ROWS; ++w) {
+            xn[w] = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) xn[w] = fmaf(r[w][j], r[w][j], xn[w]);
+            if (a.res) {
+                // each of the row's four threads writes a quarter of the columns; the quarter is selected by an unrolled compare
+                // so that r[][] keeps compile-time indices (a run-time index would push the whole array to local memory)
+#pragma unroll
+                for (int qq = 0; qq < RQ_SPLIT; ++qq) {
+                    if (q != qq) continue;
+#pragma unroll
+                    for (int jj = 0; jj < JQ; ++jj) {
+                        const int j = qq * JQ + jj;
+                        if (STAGE) st_res[((size_t)(w * RQ_ROWS_PER_CTA + rl) * D + j) * a.levels + l] = r[w][j];
+                        else if (live[w]) a.res[(row[w] * D + j) * a.levels + l] = r[w][j];
+                    }
+                }
+            }
+            best[w] = INFINITY;
+            best_k[w] = 0;
+        }
+        const int k_lo = q * kq;
+        for (int k = k_lo; k < k_lo + kq; k += 2) {
+            float d0[ROWS], d1[ROWS];
+#pragma unroll
+            for (int w = 0; w < ROWS; ++w) d0[w] = d1[w] = 0.f;
+            const float4* c0 = reinterpret_cast<const float4*>(cb + k * D);
+            const float4* c1 = reinterpret_cast<const float4*>(cb + (k + 1) * D);
+#pragma unroll
+            for (int j = 0; j < D / 4; ++j) {
+                const float4 u = c0[j], v = c1[j];
+#pragma unroll
+                for (int w = 0; w < ROWS; ++w) {
+                    d0[w] = fmaf(r[w][4 * j], u.x, d0[w]); d0[w] = fmaf(r[w][4 * j + 1], u.y, d0[w]);
+                    d0[w] = fmaf(r[w][4 * j + 2], u.z, d0[w]); d0[w] = fmaf(r[w][4 * j + 3], u.w, d0[w]);
+                    d1[w] = fmaf(r[w][4 * j], v.x, d1[w]); d1[w] = fmaf(r[w][4 * j + 1], v.y, d1[w]);
+                    d1[w] = fmaf(r[w][4 * j + 2], v.z, d1[w]); d1[w] = fmaf(r[w][4 * j + 3], v.w, d1[w]);
+                }
+            }
+            const float n0 = cn[k], n1 = cn[k + 1];
+#pragma unroll
+            for (int w = 0; w < ROWS; ++w) {
+                const float dist0 = (xn[w] + n0) - 2.f * d0[w];
+                const float dist1 = (xn[w] + n1) - 2.f * d1[w];
+                if (dist0 < best[w]) { best[w] = dist0; best_k[w] = k; }
+                if (dist1 < best[w]) { best[w] = dist1; best_k[w] = k + 1; }
+            }
+        }
+        // the four quarters of a row sit in lanes (lane & 7) + {0, 8, 16, 24}
+#pragma unroll
+        for (int w = 0; w < ROWS; ++w) {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best[w], o);
+                const int ok = __shfl_xor_sync(0xffffffffu, best_k[w], o);
+                if (ob < best[w] || (ob == best[w] && ok < best_k[w])) { best[w] = ob; best_k[w] = ok; }
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < ROWS; ++w) {
+            float sq = 0.f;
+            const float* cw = cb + best_k[w] * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float e = cw[j];
+                r[w][j] -= e;
+                sq = fmaf(r[w][j], r[w][j], sq);
+            }
+            if (a.emb) {
+#pragma unroll
+                for (int jj = 0; jj < JQ; ++jj) {
+                    const int j = q * JQ + jj;
+                    if (STAGE) st_emb[((size_t)(w * RQ_ROWS_PER_CTA + rl) * D + j) * a.levels + l] = cw[j];
+                    else if (live[w]) a.emb[(row[w] * D + j) * a.levels + l] = cw[j];
+                }
+            }
+            loss[w] += sq + a.commitment * sq;
+            if (live[w] && q == 0) a.ids[row[w] * a.levels + l] = best_k[w];
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < ROWS; ++w) {
+        if (!live[w] || q != 0) continue;
+        if (a.loss) a.loss[row[w]] = loss[w];
+        if (a.res_out) {
+#pragma unroll
+            for (int j = 0; j < D; j += 4)
+                *reinterpret_cast<float4*>(a.res_out + row[w] * D + j) = make_float4(r[w][j], r[w][j + 1], r[w][j + 2], r[w][j + 3]);
+        }
+    }
+    if (STAGE && (a.emb || a.res)) {
+        // staged rows -> global: ROWS slabs of RQ_ROWS_PER_CTA consecutive rows, each slab one contiguous span
+        __syncthreads();
+        const int per_row = D * a.levels;              // floats, a multiple of 4
+#pragma unroll
+        for (int w = 0; w < ROWS; ++w) {
+            const long long first = row0 + (long long)w * RQ_ROWS_PER_CTA;
+            long long nrows = a.N - first;
+            if (nrows <= 0) continue;
+            if (nrows > RQ_ROWS_PER_CTA) nrows = RQ_ROWS_PER_CTA;
+            const size_t nfl = (size_t)nrows * per_row;
+            const float* s_e = st_emb + (size_t)w * RQ_ROWS_PER_CTA * per_row;
+            const float* s_r = st_res + (size_t)w * RQ_ROWS_PER_CTA * per_row;
+            for (size_t i = (size_t)tid * 4; i < nfl; i += RQ_THREADS * 4) {
+                if (a.emb) *reinterpret_cast<float4*>(a.emb + (size_t)first * per_row + i) = *reinterpret_cast<const float4*>(s_e + i);
+                if (a.res) *reinterpret_cast<float4*>(a.res + (size_t)first * per_row + i) = *reinterpret_cast<const float4*>(s_r + i);
+            }
+        }
+    }
+}
+
 }  // namespace grb

@@ -526,6 +526,20 @@ struct TcEpiF32 {
         }
     }
 };
+// out = ACT(acc) -> fp32   (ACT 0: none, 1: silu) - the bias-free MLP layers of the RQ-VAE encoder (fp32-accurate split-bf16 GEMM)
+template <int ACT>
+struct TcEpiActF32 {
+    static constexpr int kOut = 3;
+    static constexpr bool kPre = false;
+    static constexpr bool kAux = false;
+    GRB_DEVINL void prepare() {}
+    GRB_DEVINL void operator()(int, int, float (&v)[32], float (&)[32], int) const {
+        if (ACT == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+        }
+    }
+};
 // out += scale * acc (split-K partial sums, weight gradients)
 struct TcEpiAtomicF32 {
     static constexpr int kOut = 0;

@@ -317,6 +317,22 @@ def head_logits(x, ln_g, ln_b, table, table_bf16, eps) -> torch.Tensor:
     return logits
 
 
+def eval_rank_metrics(logits_last: torch.Tensor, targets: torch.Tensor, metrics: Optional[torch.Tensor] = None,
+                      want_ranks: bool = False):
+    """logits_last [B, C] fp32, targets [B] int64 -> metrics [6] fp32 accumulated on the device:
+    Recall@{1,5,10} hit counts, NDCG@{1,5,10} sums (hstu_trainer.py:55-81 without the per-sample host loop)."""
+    require_cuda(logits_last, targets)
+    require_i64(targets)
+    lg = logits_last.detach().contiguous().float()
+    B, Cn = lg.shape
+    if metrics is None:
+        metrics = torch.zeros(6, dtype=torch.float32, device=lg.device)
+    ranks = torch.empty(B, dtype=torch.int32, device=lg.device) if want_ranks else None
+    with torch.cuda.device(lg.device):
+        check(_lib.load().grb_eval_rank_metrics(ptr(lg), ptr(targets.contiguous()), B, Cn, ptr(metrics), ptr(ranks), stream_ptr(lg.device)))
+    return (metrics, ranks) if want_ranks else metrics
+
+
 # ------------------------------------------------------------------------------------------------ attention core alone
 def hstu_attention_fwd(P: torch.Tensor, meta: SeqMeta, H: int, pos_table: torch.Tensor, time_table: Optional[torch.Tensor],
                        ntime: int = 64) -> torch.Tensor:
@@ -474,6 +490,29 @@ def rq_residual_argmin(x: torch.Tensor, codebooks: torch.Tensor, commitment: flo
         check(lib.grb_rq_residual_argmin(ptr(x), ptr(cb), N, D, K, levels, float(commitment), ptr(ids), ptr(emb), ptr(res), ptr(loss), None,
                                          stream_ptr(x.device)))
     return ids, emb, res, loss
+
+
+def split3(x: torch.Tensor, operand: int) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 [rows, 6K]: the three-term bf16 split of every value, laid out along K for the fp32-accurate GEMM
+    (operand 0 = activation layout, 1 = weight layout; csrc/rowwise.cuh split3_f32_bf16_kernel)."""
+    require_cuda(x)
+    require_f32(x)
+    x = x.detach().contiguous()
+    rows, K = x.numel() // x.shape[-1], x.shape[-1]
+    out = torch.empty(*x.shape[:-1], 6 * K, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grb_split3_f32_to_bf16(ptr(x), ptr(out), rows, K, operand, stream_ptr(x.device)))
+    return out
+
+
+def linear_f32x3(x_split: torch.Tensor, w_split: torch.Tensor, act: int = 0) -> torch.Tensor:
+    """y = act(x W^T) in fp32 accuracy on the tcgen05 path; x_split [T, 6K], w_split [N, 6K] from split3(); act 0 none, 1 silu."""
+    K6 = x_split.shape[-1]
+    T, N = x_split.numel() // K6, w_split.shape[0]
+    y = torch.empty(*x_split.shape[:-1], N, dtype=torch.float32, device=x_split.device)
+    with torch.cuda.device(x_split.device):
+        check(_lib.load().grb_linear_f32x3_forward(ptr(x_split), ptr(w_split), T, N, K6 // 6, act, ptr(y), stream_ptr(x_split.device)))
+    return y
 
 
 def adam_step(p, g, m, v, p_bf16, state, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, zero_grad=True):

@@ -315,6 +315,22 @@ class HSTU(nn.Module):
         return logits, loss
 
     @torch.no_grad()
+    def last_logits(self, input_ids: torch.Tensor, timestamps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, V+1] fp32 logits of the LAST position only (all that predict() / evaluation read): the tied-embedding GEMM runs
+        on B rows instead of B*L."""
+        x = self.encode(input_ids, timestamps)
+        return Fn.head_logits(x[:, -1:, :].contiguous(), self.final_norm.weight, self.final_norm.bias, self.item_embedding.weight,
+                              self._table_mirror(), self.final_norm.eps)[:, 0, :]
+
+    @torch.no_grad()
+    def evaluate_batch(self, input_ids: torch.Tensor, timestamps: Optional[torch.Tensor], targets: torch.Tensor,
+                       metrics: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Leave-one-out metrics of one evaluation batch, accumulated ON THE DEVICE into ``metrics`` ([6] fp32: Recall@{1,5,10} hit
+        counts, NDCG@{1,5,10} sums) - the loop of genrec/trainers/hstu_trainer.py:55-81 without per-sample ``.item()`` calls.
+        Divide by the number of samples (and all-reduce across ranks) once at the end of the evaluation."""
+        return Fn.eval_rank_metrics(self.last_logits(input_ids, timestamps), targets, metrics)
+
+    @torch.no_grad()
     def predict(self, input_ids: torch.Tensor, timestamps: Optional[torch.Tensor] = None, top_k: int = 10) -> torch.Tensor:
         """hstu.py:150-157."""
         logits, _ = self.forward(input_ids, timestamps)

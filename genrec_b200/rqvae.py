@@ -60,9 +60,34 @@ class MLP(nn.Module):
                 self.mlp.append(nn.SiLU())
         self.mlp.append(nn.Identity())
 
+    def _split_weights(self):
+        """bf16 three-term splits of the layer weights (weight layout of the fp32-accurate GEMM), cached per parameter version."""
+        lins = [m for m in self.mlp if isinstance(m, nn.Linear)]
+        key = tuple((w.weight._version, w.weight.data_ptr()) for w in lins)
+        if getattr(self, "_split_key", None) != key:
+            self._split = [Fn.split3(w.weight, 1) for w in lins]
+            self._split_key = key
+        return self._split
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         assert x.shape[-1] == self.input_dim, f"Invalid input dim: Expected {self.input_dim}, found {x.shape[-1]}"
-        return self.mlp(x)
+        if x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            # inference (get_semantic_ids): every layer is one tcgen05 GEMM on three-term bf16 splits of both operands with the
+            # SiLU in its epilogue - fp32 accuracy (the semantic ids must not depend on a bf16 rounding of the latent)
+            ws = self._split_weights()
+            h = x.detach().float().contiguous()
+            for i, w in enumerate(ws):
+                h = Fn.linear_f32x3(Fn.split3(h, 0), w, act=1 if i != len(ws) - 1 else 0)
+            return h
+        return self.mlp(x)     # training of the encoder (autograd) stays on the library GEMM: out of scope of the hot path
+
+
+def _rotation_trick(u: torch.Tensor, q: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
+    """genrec/models/rqvae.py:67-83 (efficient_rotation_trick_transform): rotate e from direction u onto direction q without
+    forming the rotation matrix; u, q unit vectors [N, D], gradients flow through e only."""
+    e = e.unsqueeze(1)                                            # [N, 1, D]
+    w = F.normalize(u + q, p=2, dim=1, eps=1e-6).detach()
+    return (e - 2 * (e @ w.unsqueeze(-1) @ w.unsqueeze(1)) + 2 * (e @ u.unsqueeze(-1).detach() @ q.unsqueeze(1).detach())).squeeze()
 
 
 class Quantize(nn.Module):
@@ -96,12 +121,32 @@ class Quantize(nn.Module):
 
     def forward(self, x: torch.Tensor, temperature=None) -> QuantizeOutput:
         assert x.shape[-1] == self.embed_dim
-        if self.training:
-            raise NotImplementedError("training-mode quantisation estimators are out of scope (SURVEY.md section 8, row a10)")
         require_cuda(x)
         ensure_device(x.device)
-        ids, emb, _res, loss = Fn.rq_residual_argmin(x, self.embedding.weight.unsqueeze(0), self.commitment_weight)
-        return QuantizeOutput(embeddings=emb[:, :, 0], ids=ids[:, 0], loss=loss)
+        if not self.training:
+            ids, emb, _res, loss = Fn.rq_residual_argmin(x, self.embedding.weight.unsqueeze(0), self.commitment_weight)
+            return QuantizeOutput(embeddings=emb[:, :, 0], ids=ids[:, 0], loss=loss)
+        # training (rqvae.py:201-245): the nearest-code search is the CUDA kernel (ids are not differentiated, `dist.detach()`
+        # at rqvae.py:199); the estimator around it is the reference's element-wise formula on [N, D] tensors
+        ids = Fn.rq_residual_argmin(x, self.embedding.weight.unsqueeze(0), self.commitment_weight, want_aux=False)[0][:, 0]
+        codebook = self.embedding.weight
+        if self.forward_mode == QuantizeForwardMode.STE:                                     # rqvae.py:207-209
+            emb = self.get_item_embeddings(ids)
+            emb_out = x + (emb - x).detach()
+        elif self.forward_mode == QuantizeForwardMode.ROTATION_TRICK:                        # rqvae.py:210-216
+            emb = self.get_item_embeddings(ids)
+            emb_out = _rotation_trick(x / (x.norm(dim=-1, keepdim=True) + 1e-8), emb / (emb.norm(dim=-1, keepdim=True) + 1e-8), x)
+        elif self.forward_mode == QuantizeForwardMode.GUMBEL_SOFTMAX:                        # rqvae.py:201-206
+            dist = (x ** 2).sum(1, keepdim=True) + (codebook.T ** 2).sum(0, keepdim=True) - 2 * x @ codebook.T
+            u = torch.rand(dist.shape, device=x.device)
+            y = -dist + -torch.log(-torch.log(u + 1e-20) + 1e-20)                            # modules/gumbel.py:10-46
+            emb = F.softmax(y / temperature, dim=-1) @ codebook
+            emb_out = emb
+        else:
+            raise NotImplementedError("the Sinkhorn estimator (fp64, 100 iterations) is out of scope (SURVEY.md section 8, row f3)")
+        emb_loss = ((x.detach() - emb) ** 2).sum(-1)                                          # modules/loss.py:75-77
+        query_loss = ((x - emb.detach()) ** 2).sum(-1)
+        return QuantizeOutput(embeddings=emb_out, ids=ids, loss=emb_loss + self.commitment_weight * query_loss)
 
 
 class RqVae(nn.Module):

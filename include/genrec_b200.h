@@ -144,6 +144,12 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
 int grb_head_logits(const float* x, const float* ln_g, const float* ln_b, float ln_eps, const void* table_bf16, int T,
                     int D, int C, float* logits, void* workspace, void* stream);
 
+/* Leave-one-out evaluation without host round trips (replaces the per-sample loop of genrec/trainers/hstu_trainer.py:55-81):
+ * logits [B, C] fp32 of the LAST position, targets [B] (0 = skip).  The rank of the target among classes 1..C-1 (class 0 is
+ * excluded as the trainer's `logits[:, 0] = -inf` does) is counted on the device and the metric sums are ACCUMULATED:
+ * metrics[0..2] += Recall@{1,5,10} hits, metrics[3..5] += NDCG@{1,5,10}.  ranks [B] int32 is optional. */
+int grb_eval_rank_metrics(const float* logits, const int64_t* targets, int B, int C, float* metrics, int32_t* ranks, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ SASRec attention
  * Replaces MultiHeadAttention.forward (genrec/models/sasrec.py:192-246) after the three projections:
  *   out = softmax_j(mask(Q K^T * dh^-1/2)) * query_mask @ V     (residual and projections are GEMM epilogues) */
@@ -179,6 +185,14 @@ int grb_layernorm_forward(const float* x, const float* g, const float* b, float 
                           float* y_f32, float* stats, void* stream);
 int grb_layernorm_backward(const float* dy, const float* x, const float* stats, const float* g, const float* residual,
                            int T, int D, float* dx, float* dg, float* db, void* stream);
+
+/* fp32-accurate linear layer on the bf16 tensor path (the RQ-VAE encoder MLP, genrec/modules/encoder.py:399-420: bias-free
+ * Linear + SiLU).  Operands are split into three bf16 terms each and the six significant cross terms are laid out along K
+ * (K' = 6 K), so one tcgen05 GEMM with fp32 accumulation reproduces the fp32 product to ~2^-22 relative.
+ *   grb_split3_f32_to_bf16: in [rows, K] fp32 -> out [rows, 6 K] bf16 ; operand 0 = activation (A) layout, 1 = weight (B) layout
+ *   grb_linear_f32x3_forward: y [T, N] fp32 = act(x [T, K] @ W [N, K]^T), both operands pre-split ; act 0 none, 1 silu */
+int grb_split3_f32_to_bf16(const float* in, void* out_bf16, size_t rows, int K, int operand, void* stream);
+int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16, int T, int N, int K, int act, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ optimizer / casts */
 int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);

@@ -74,8 +74,8 @@ def test_rqvae_mirror_schema(golden):
     assert m.codebooks().shape == (3, 256, 32)
     with pytest.raises(RuntimeError):
         m.eval().get_semantic_ids(g["x"])       # CPU tensors: no fallback
-    with pytest.raises(NotImplementedError):
-        m.train().layers[0](torch.zeros(2, 32), 0.1)
+    with pytest.raises(RuntimeError):
+        m.train().layers[0](torch.zeros(2, 32), 0.1)     # training-mode quantisation runs the CUDA search too: CPU tensors raise
 
 
 def test_genrec_shim_import_paths():
@@ -85,6 +85,35 @@ def test_genrec_shim_import_paths():
     import genrec_b200.hstu as ours
     assert hstu.HSTU is ours.HSTU and hstu.HSTULayer is ours.HSTULayer
     assert hasattr(rq, "RqVae") and hasattr(rq, "Quantize") and hasattr(rq, "QuantizeForwardMode")
+    # the two import lines of config/hstu/amazon.gin:5-6 and of config/sasrec/amazon.gin resolve with this repository alone
+    dh = importlib.import_module("genrec.data.amazon_hstu")
+    ds = importlib.import_module("genrec.data.amazon_sasrec")
+    assert callable(dh.hstu_collate_fn) and callable(dh.hstu_eval_collate_fn) and callable(ds.sasrec_collate_fn)
+    models = importlib.import_module("genrec.models")          # what genrec/models/__init__.py of the reference exports for this path
+    for name in ("HSTU", "SASRec", "RqVae", "QuantizeForwardMode"):
+        assert hasattr(models, name), name
+
+
+def test_genrec_shim_extends_the_reference_package_instead_of_shadowing_it(tmp_path, monkeypatch):
+    """With a reference checkout further down sys.path, modules this repository does not provide still resolve there."""
+    import importlib
+    import sys
+    ref = tmp_path / "refcheckout" / "genrec"
+    (ref / "trainers").mkdir(parents=True)
+    (ref / "models").mkdir()
+    (ref / "__init__.py").write_text("raise RuntimeError('the shim package must win')\n")
+    (ref / "trainers" / "__init__.py").write_text("")
+    (ref / "trainers" / "hstu_trainer.py").write_text("MARK = 'reference trainer'\n")
+    (ref / "models" / "tiger.py").write_text("MARK = 'reference tiger'\n")
+    monkeypatch.syspath_prepend(str(tmp_path / "refcheckout"))          # even AHEAD of us only sub-paths are merged ...
+    for k in [k for k in sys.modules if k == "genrec" or k.startswith("genrec.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import os
+    monkeypatch.syspath_prepend(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # ... but this repository is first
+    assert importlib.import_module("genrec.trainers.hstu_trainer").MARK == "reference trainer"
+    assert importlib.import_module("genrec.models.tiger").MARK == "reference tiger"
+    import genrec_b200.hstu as ours
+    assert importlib.import_module("genrec.models.hstu").HSTU is ours.HSTU
 
 
 def test_collate_mirrors_reference_known_answers(golden):

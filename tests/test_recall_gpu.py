@@ -74,3 +74,37 @@ def test_recall_at_10_matches_oracle_training():
     assert rec_o > 0.25, rec_o                       # the task is learnable (chance = 10/200 = 0.05)
     assert abs(rec_g - rec_o) <= 0.04, (rec_g, rec_o)
     assert abs(loss_g - loss_o) <= 0.08 * abs(loss_o), (loss_g, loss_o)
+
+
+def test_device_side_metrics_match_the_trainer_loop():
+    """grb_eval_rank_metrics (Recall/NDCG accumulated on the device, no per-sample .item()) == the reference trainer's loop
+    (oracle.recall_ndcg over top-10 of the masked last-position logits), incl. skipped (target 0) samples and exact ties."""
+    from genrec_b200.hstu import HSTU
+    import genrec_b200.functional as Fn
+    from oracle import hstu as oh
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    V, L, B = 300, 30, 64
+    m = HSTU(V, L, 64, 2, 2, dropout=0.0).to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, V + 1, (B, L), generator=g).to(dev)
+    ts = (1_300_000_000 + torch.cumsum(torch.randint(1, 86400, (B, L), generator=g), 1)).to(dev)
+    tg = torch.randint(1, V + 1, (B,), generator=g).to(dev)
+    logits = m.last_logits(ids, ts)
+    full, _ = m(ids, ts)
+    torch.testing.assert_close(logits, full[:, -1, :], rtol=1e-5, atol=1e-5)
+    metrics = m.evaluate_batch(ids, ts, tg)
+    metrics = m.evaluate_batch(ids, ts, tg, metrics)            # accumulates: twice the sums
+    masked = logits.clone(); masked[:, 0] = float("-inf")
+    top = torch.topk(masked, 10, dim=-1).indices.cpu()
+    ref = oh.recall_ndcg(top, tg.cpu())
+    want = torch.tensor([ref["Recall@1"], ref["Recall@5"], ref["Recall@10"], ref["NDCG@1"], ref["NDCG@5"], ref["NDCG@10"]])
+    torch.testing.assert_close(metrics.cpu(), 2 * want, rtol=1e-5, atol=1e-5)
+    # ties + skipped samples on hand-made logits
+    lg = torch.zeros(3, 8, device=dev)
+    lg[0, 5] = 1.0; lg[0, 2] = 1.0          # target 5 ties with class 2 (lower index ranks first) -> rank 2
+    lg[1, 0] = 9.0; lg[1, 3] = 2.0          # class 0 is excluded -> target 3 has rank 1
+    met, ranks = Fn.eval_rank_metrics(lg, torch.tensor([5, 3, 0], device=dev), want_ranks=True)
+    assert ranks.tolist() == [2, 1, 0]
+    torch.testing.assert_close(met.cpu(), torch.tensor([1.0, 2.0, 2.0, 1.0, 1.0 + 1 / torch.log2(torch.tensor(3.0)).item(),
+                                                        1.0 + 1 / torch.log2(torch.tensor(3.0)).item()]))

@@ -65,3 +65,91 @@ def test_rq_empty_and_errors():
         Fn.rq_residual_argmin(torch.zeros(4, 48, device=dev), torch.rand(3, 256, 48, device=dev))
     with pytest.raises(RuntimeError):
         Fn.rq_residual_argmin(torch.zeros(4, 32), torch.rand(3, 256, 32))
+
+
+@pytest.mark.parametrize("N,D,levels", [(12101, 32, 3), (777, 64, 5), (200_000, 32, 3)])
+def test_rq_split_kernel_equals_one_thread_per_row_kernel(N, D, levels, monkeypatch):
+    """The four-threads-per-row kernel keeps the arithmetic of the first-generation kernel (same dot-product order, same tie
+    rule): every output is bit-identical, including the staged [N, D, levels] writes."""
+    import genrec_b200.functional as Fn
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N % 997 + D)
+    x = torch.randn(N, D, generator=g).to(dev)
+    cbs = torch.stack([(torch.rand(256, D, generator=g) - 0.5) * (2.0 / 2 ** l) for l in range(levels)])
+    cbs[0, 200] = cbs[0, 17]                       # exact ties: the first index must win in both
+    cbs = cbs.to(dev)
+    out = {}
+    for mode in ("split", "thread"):
+        monkeypatch.setenv("GRB_RQ", mode)
+        out[mode] = Fn.rq_residual_argmin(x, cbs, 0.25)
+    for a, b in zip(out["split"], out["thread"]):
+        assert torch.equal(a, b)
+    ids_only = Fn.rq_residual_argmin(x, cbs, 0.25, want_aux=False)[0]
+    assert torch.equal(ids_only, out["split"][0])
+
+
+def test_rq_encoder_fp32_accurate_tensor_path(golden):
+    """RqVae.encode at inference = five tcgen05 GEMMs on three-term bf16 splits (SiLU in the epilogue): fp32 accuracy against the
+    oracle's fp32 MLP, and the semantic ids of the reference golden end to end."""
+    from genrec_b200.rqvae import RqVae
+    from oracle import rqvae as orq
+    g = golden("rqvae_3x256x32.pt")
+    cfg = g["cfg"]
+    dev = torch.device("cuda:0")
+    m = RqVae(cfg["input_dim"], cfg["D"], cfg["hidden_dims"], cfg["K"], codebook_kmeans_init=False, n_layers=cfg["levels"], n_cat_features=0)
+    m.load_state_dict(g["state_dict"], strict=False)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        lat = m.encode(g["x"].to(dev)).cpu()
+    torch.testing.assert_close(lat, g["latent"], rtol=2e-5, atol=2e-6)
+    out = m.get_semantic_ids(g["x"].to(dev))
+    agree = (out.sem_ids.cpu() == g["sem_ids"]).all(1).float().mean().item()
+    assert agree >= 0.995, agree
+    # the production geometry: 768 -> 512 -> 256 -> 128 -> 64 -> 32 on 12,101 items
+    torch.manual_seed(0)
+    big = RqVae(768, 32, [512, 256, 128, 64], 256, codebook_kmeans_init=False, n_layers=3, n_cat_features=0).to(dev).eval()
+    x = torch.randn(12101, 768)
+    x = x / x.norm(dim=1, keepdim=True)
+    ws = [l.weight.detach().cpu() for l in big.encoder.mlp if isinstance(l, torch.nn.Linear)]
+    ref = orq.mlp_encoder(x.double(), [w.double() for w in ws]).float()
+    with torch.no_grad():
+        got = big.encode(x.to(dev)).cpu()
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("mode", ["STE", "ROTATION_TRICK", "GUMBEL_SOFTMAX"])
+def test_quantize_training_mode_matches_reference_formulas(mode):
+    """Training-mode Quantize.forward (rqvae.py:201-245): ids from the CUDA search, estimator = the reference's formulas."""
+    from genrec_b200.rqvae import Quantize, QuantizeForwardMode
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    q = Quantize(32, 256, do_kmeans_init=False, forward_mode=QuantizeForwardMode[mode]).to(dev).train()
+    x = torch.randn(500, 32, device=dev, requires_grad=True)
+    out = q(x, 0.2)
+    assert out.embeddings.shape == (500, 32) and out.ids.shape == (500,) and out.loss.shape == (500,)
+    # ids: nearest code (fp64 check of optimality)
+    d = torch.cdist(x.detach().double(), q.embedding.weight.detach().double()) ** 2
+    assert (d.gather(1, out.ids[:, None]).squeeze(1) <= d.min(1).values + 1e-5).all()
+    (out.embeddings.sum() + out.loss.sum()).backward()
+    assert torch.isfinite(x.grad).all() and q.embedding.weight.grad is not None
+    if mode == "GUMBEL_SOFTMAX":
+        return
+    # reference formulas on the CPU with the same ids
+    xc = x.detach().cpu().requires_grad_(True)
+    cb = q.embedding.weight.detach().cpu().requires_grad_(True)
+    emb = cb[out.ids.cpu()]
+    if mode == "STE":
+        emb_out = xc + (emb - xc).detach()
+    else:
+        u = xc / (xc.norm(dim=-1, keepdim=True) + 1e-8)
+        qq = emb / (emb.norm(dim=-1, keepdim=True) + 1e-8)
+        w = torch.nn.functional.normalize(u + qq, p=2, dim=1, eps=1e-6).detach()
+        e = xc.unsqueeze(1)
+        emb_out = (e - 2 * (e @ w.unsqueeze(-1) @ w.unsqueeze(1)) + 2 * (e @ u.unsqueeze(-1).detach() @ qq.unsqueeze(1).detach())).squeeze()
+    loss = ((xc.detach() - emb) ** 2).sum(-1) + 0.25 * ((xc - emb.detach()) ** 2).sum(-1)
+    (emb_out.sum() + loss.sum()).backward()
+    torch.testing.assert_close(out.embeddings.detach().cpu(), emb_out.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out.loss.detach().cpu(), loss.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(x.grad.cpu(), xc.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(q.embedding.weight.grad.cpu(), cb.grad, rtol=1e-4, atol=1e-5)
