@@ -186,3 +186,36 @@ def test_layer_tc_attention_matches_mma_attention(B, L, D, H, monkeypatch):
     assert relerr(dx0, dx1) < 6e-3, relerr(dx0, dx1)
     for n in g0:
         assert relerr(g0[n], g1[n]) < 8e-3, (n, relerr(g0[n], g1[n]))
+
+
+def test_custom_op_block_equals_module_block():
+    """torch.ops.genrec_b200.hstu_layer (dispatcher-registered custom op with a registered autograd formula) == HSTULayer."""
+    import genrec_b200.ops  # noqa: F401
+    from genrec_b200.hstu import HSTULayer, _thresholds_on
+    from tests.util import make_batch
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    B, L, D, H = 3, 70, 128, 4
+    layer = HSTULayer(D, H, 0.0, 32, 64, 128, True).to(dev).train()
+    with torch.no_grad():
+        for n, p in layer.named_parameters():
+            if "attention_bias" in n:
+                p.normal_(0, 0.5)
+    ids, ts, _ = make_batch(B, L, 50, seed=2)
+    ids, ts = ids.to(dev), ts.to(dev)
+    x = torch.randn(B, L, D, device=dev)
+    dy = torch.randn(B, L, D, device=dev)
+    xi = x.clone().requires_grad_(True)
+    y = layer(xi, None, ids == 0, ts)
+    y.backward(dy)
+    ref = (y.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in layer._params()])
+    layer.zero_grad(set_to_none=True)
+    pad = (ids == 0).to(torch.uint8)
+    rel, wide = torch.ops.genrec_b200.hstu_seq_prepare(ts, pad)
+    xj = x.clone().requires_grad_(True)
+    y2, _saved = torch.ops.genrec_b200.hstu_layer(xj, pad, ts, rel, wide, _thresholds_on(dev), *layer._params(), H, 64, 0, 0.0, 0, None, 0)
+    y2.backward(dy)
+    torch.testing.assert_close(y2, ref[0], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(xj.grad, ref[1], rtol=1e-4, atol=1e-5)
+    for p, g in zip(layer._params(), ref[2]):
+        torch.testing.assert_close(p.grad, g, rtol=2e-3, atol=1e-4 * max(1.0, g.abs().max().item()))
