@@ -96,6 +96,8 @@ SIGNATURES = {
     "grb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,
                               c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "grb_assert_unit_scalar": (c_int, [c_void_p, c_void_p]),
+    "grb_dp_adam_step": (c_int, [c_void_p] * 14 + [c_size_t, c_int, c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                                 c_void_p]),
     "grb_rq_residual_argmin": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -13,6 +13,7 @@
 #include "attn_sasrec.cuh"
 #include "attn_tc.cuh"
 #include "common.cuh"
+#include "dp_adam.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 #include "rq_argmin.cuh"
@@ -1013,6 +1014,37 @@ int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n
     if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
     launch_k(adam_step_kernel, (unsigned)blocks, 256, 0, st, a);
     GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int grb_dp_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, const void* mc_g, void* mc_p, void* mc_p_bf16,
+                     const void* peer_g, const void* peer_p, const void* peer_p_bf16, const void* peer_sig, void* sig, void* epoch,
+                     size_t n, int rank, int world, float* state, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float grad_scale, void* stream) {
+    GRB_REQUIRE(p && g && m && v && p_bf16 && peer_sig && sig && epoch && state, "null argument");
+    GRB_REQUIRE(world >= 2 && world <= 32 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
+    GRB_REQUIRE(n > 0 && n % ((size_t)8 * world) == 0, "n must be a multiple of 8 * world");
+    const bool mc = mc_g != nullptr && mc_p != nullptr && mc_p_bf16 != nullptr;
+    GRB_REQUIRE(mc || (peer_g && peer_p && peer_p_bf16), "neither multicast addresses nor peer pointer arrays given");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    launch_k(adam_tick_kernel, 1, 1, 0, st, state, beta1, beta2);
+    GRB_CUDA(cudaGetLastError());
+    launch_k(dp_barrier_kernel, 1, 32, 0, st, reinterpret_cast<unsigned* const*>(peer_sig), reinterpret_cast<unsigned*>(sig),
+             reinterpret_cast<unsigned*>(epoch), rank, world, 0);
+    GRB_CUDA(cudaGetLastError());
+    DpAdamArgs a{p, g, m, v, (bf16*)p_bf16, (const float*)mc_g, (float*)mc_p, (bf16*)mc_p_bf16,
+                 reinterpret_cast<const float* const*>(peer_g), reinterpret_cast<float* const*>(peer_p), reinterpret_cast<bf16* const*>(peer_p_bf16),
+                 n, rank, world, state, lr, beta1, beta2, eps, weight_decay, grad_scale};
+    size_t blocks = (n / world / 8 + 255) / 256;
+    if (blocks > (size_t)sm_count() * 4) blocks = (size_t)sm_count() * 4;
+    if (blocks < 1) blocks = 1;
+    if (mc) launch_k(dp_adam_kernel<true>, (unsigned)blocks, 256, 0, st, a);
+    else launch_k(dp_adam_kernel<false>, (unsigned)blocks, 256, 0, st, a);
+    GRB_CUDA(cudaGetLastError());
+    launch_k(dp_barrier_kernel, 1, 32, 0, st, reinterpret_cast<unsigned* const*>(peer_sig), reinterpret_cast<unsigned*>(sig),
+             reinterpret_cast<unsigned*>(epoch), rank, world, 1);
+    GRB_CUDA(cudaGetLastError());
+    GRB_CUDA(cudaMemsetAsync(g, 0, n * sizeof(float), st));
     return 0;
 }
 

@@ -81,17 +81,18 @@ GRB_DEVINL uint64_t atc_kmaj(uint32_t addr) { return umma_desc(addr, 16, 1024); 
 GRB_DEVINL uint64_t atc_mnmaj(uint32_t addr) { return umma_desc(addr, ATC_BOX_BYTES, 1024); }  // MN-major, next 64-wide block one box away
 
 // ------------------------------------------------------------------------------------------------ per-sequence pre-pass
-// rel[b, i] = int32(ts[b, i] - min over valid positions of ts[b, :]) ; wide[b] = 1 when max - min >= 2^31 (then rel is unused)
+// rel[b, i] = int32(ts[b, i] - min_i ts[b, :]) ; wide[b] = 1 when max - min >= 2^31 (then rel is unused).  Padded positions take
+// part: a padded QUERY row still attends to earlier real keys with its own timestamp (hstu.py:400 does not look at the pad mask), so
+// with the usual "pads carry 0" convention the span is the largest real timestamp - fine for second-resolution data until 2038.
 __global__ void __launch_bounds__(256) hstu_seq_prep_kernel(const long long* __restrict__ ts, const uint8_t* __restrict__ pad, int L,
                                                            int* __restrict__ rel, uint8_t* __restrict__ wide) {
     pdl_wait();
+    (void)pad;
     __shared__ long long s_min[8], s_max[8];
     const int b = blockIdx.x;
     const long long* t = ts + (size_t)b * L;
-    const uint8_t* p = pad + (size_t)b * L;
     long long mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
-    for (int i = threadIdx.x; i < L; i += 256)
-        if (!p[i]) { const long long v = t[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    for (int i = threadIdx.x; i < L; i += 256) { const long long v = t[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const long long a = __shfl_xor_sync(0xffffffffu, mn, o), c = __shfl_xor_sync(0xffffffffu, mx, o);
@@ -102,12 +103,11 @@ __global__ void __launch_bounds__(256) hstu_seq_prep_kernel(const long long* __r
     mn = s_min[0]; mx = s_max[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) { mn = s_min[w] < mn ? s_min[w] : mn; mx = s_max[w] > mx ? s_max[w] : mx; }
-    const bool any_valid = mx >= mn;
     // span computed in unsigned arithmetic: mx - mn of two int64 may not fit int64
-    const unsigned long long span = any_valid ? (unsigned long long)mx - (unsigned long long)mn : 0ull;
+    const unsigned long long span = (unsigned long long)mx - (unsigned long long)mn;
     const bool w64 = span >= (1ull << 31);
     if (threadIdx.x == 0) wide[b] = w64 ? 1 : 0;
-    for (int i = threadIdx.x; i < L; i += 256) rel[(size_t)b * L + i] = (p[i] || w64) ? 0 : (int)(t[i] - mn);
+    for (int i = threadIdx.x; i < L; i += 256) rel[(size_t)b * L + i] = w64 ? 0 : (int)(t[i] - mn);
 }
 
 // ------------------------------------------------------------------------------------------------ bucket bytes of 32 cells
@@ -117,21 +117,27 @@ template <bool WIDE, bool MASKED>
 GRB_DEVINL void atc_buckets(uint32_t (&bk)[8], int i, int j0, int ri, long long ti, const int* s_rel, const long long* s_ts,
                             const uint8_t* s_pad, const uint32_t* s_thr32, const long long* s_thr64, int ntime, int L, bool row_ok) {
     const int ntm1 = ntime - 1;
+    const bool clamp = ntm1 < 31;     // 32-bit differences never reach bucket 32 (warp-uniform)
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         uint32_t word = 0;
+        int rj[4] = {0, 0, 0, 0};
+        if (!WIDE) {
+            const int4 r4 = *reinterpret_cast<const int4*>(s_rel + 4 * w);      // four keys per broadcast LDS.128
+            rj[0] = r4.x; rj[1] = r4.y; rj[2] = r4.z; rj[3] = r4.w;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = w * 4 + q;
             int b = 0;
             if (ntime > 0) {
                 if (!WIDE) {
-                    const int d = ri - s_rel[k];
-                    unsigned dd = d < 0 ? (unsigned)(-d) : (unsigned)d;
-                    dd = dd < 1u ? 1u : dd;
-                    const int e = 31 - __clz(dd);
-                    b = e + (dd >= s_thr32[e + 1] ? 1 : 0);
-                    b = b < ntm1 ? b : ntm1;
+                    // e = floor(log2 |d|) (-1 for d == 0: thr32[0] == 0 then gives bucket 0) ; bucket = e + (|d| >= thr[e + 1])
+                    const int d = ri - rj[q];
+                    const unsigned a = (unsigned)(d < 0 ? -d : d);
+                    const int e = 31 - __clz(a);
+                    b = e + (a >= s_thr32[e + 1] ? 1 : 0);
+                    if (clamp) b = b < ntm1 ? b : ntm1;
                 } else {
                     b = time_bucket_dev(ti - s_ts[k], s_thr64, ntime);
                 }
@@ -195,9 +201,9 @@ template <int DH>
 struct AtcFwdSmem {
     static constexpr int HB = 64 / DH;
     static constexpr int kQ = 0;
-    static constexpr int kK = ATC_BOX_BYTES;                       // [2 stages]
-    static constexpr int kV = kK + 2 * ATC_BOX_BYTES;              // [2 stages]
-    static constexpr int kP = kV + 2 * ATC_BOX_BYTES;
+    static constexpr int kK = ATC_BOX_BYTES;                       // one stage: two CTAs share an SM and cover each other's loads
+    static constexpr int kV = kK + ATC_BOX_BYTES;
+    static constexpr int kP = kV + ATC_BOX_BYTES;
     static constexpr int kSmall = kP + ATC_TILE2_BYTES;
     // small area: rel[2][128] int | ts[2][128] ll | pad[2][128] | thr32[36] | thr64[65] | tbl[HB][ATC_TBL_LD] | barriers
     static constexpr int kRel = kSmall;
@@ -211,7 +217,7 @@ struct AtcFwdSmem {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(ATC_THREADS, 1) hstu_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmP, HstuTcArgs a, int nqt) {
+__global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmP, HstuTcArgs a, int nqt) {
     using SM = AtcFwdSmem<DH>;
     constexpr int HB = SM::HB, KS = DH / 16;
     extern __shared__ unsigned char atc_smem_raw[];
@@ -228,8 +234,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) hstu_attn_tc_fwd_kernel(const 
     float* s_tbl = reinterpret_cast<float*>(base + SM::kTbl);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::kBars);
     uint64_t* q_full = bars;            // TMA -> MMA
-    uint64_t* kv_full = bars + 1;       // [2]
-    uint64_t* kv_empty = bars + 3;      // [2] MMA -> TMA
+    uint64_t* kv_full = bars + 1;       // TMA -> MMA (K and V boxes of one key tile)
+    uint64_t* kv_empty = bars + 3;      // MMA -> TMA
     uint64_t* s_full = bars + 5;        // MMA -> EW : a 128 x 64 half tile of S is in TMEM
     uint64_t* s_free = bars + 6;        // EW -> MMA : ... and has been read into registers
     uint64_t* p_full = bars + 7;        // EW -> MMA : the P tile of one head is in shared memory
@@ -252,7 +258,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) hstu_attn_tc_fwd_kernel(const 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmP);
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(kv_full, 1);
+        mbar_init(kv_empty, 1);
         mbar_init(s_full, 1);
         mbar_init(s_free, ATC_EW_WARPS);
         mbar_init(p_full, ATC_EW_WARPS);
@@ -275,11 +282,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) hstu_attn_tc_fwd_kernel(const 
             mbar_expect_tx(q_full, ATC_BOX_BYTES);
             tma_load_2d(sQ, &tmP, 2 * a.D + box * 64, row_q, q_full);
             for (int kt = 0; kt < nkt; ++kt) {
-                const int st = kt & 1;
-                mbar_wait(&kv_empty[st], ((kt >> 1) & 1) ^ 1);
-                mbar_expect_tx(&kv_full[st], 2 * ATC_BOX_BYTES);
-                tma_load_2d(sK + st * ATC_BOX_BYTES, &tmP, 3 * a.D + box * 64, (int)tok0 + kt * 128, &kv_full[st]);
-                tma_load_2d(sV + st * ATC_BOX_BYTES, &tmP, a.D + box * 64, (int)tok0 + kt * 128, &kv_full[st]);
+                mbar_wait(kv_empty, (kt & 1) ^ 1);
+                mbar_expect_tx(kv_full, 2 * ATC_BOX_BYTES);
+                tma_load_2d(sK, &tmP, 3 * a.D + box * 64, (int)tok0 + kt * 128, kv_full);
+                tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + kt * 128, kv_full);
             }
         }
     } else if (warp == 1) {
@@ -294,19 +300,21 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) hstu_attn_tc_fwd_kernel(const 
             auto issue_pv = [&](int hb, int kt) {
                 mbar_wait(p_full, n & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(sV + (kt & 1) * ATC_BOX_BYTES);
+                const uint32_t v_addr = smem_u32(sV);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     umma_bf16(tm_O + hb * DH, atc_kmaj(p_addr + (ks >> 2) * ATC_BOX_BYTES + (ks & 3) * 32),
                               atc_mnmaj(v_addr + hb * DH * 2 + ks * 2048), idesc_pv, (kt > 0 || ks > 0) ? 1u : 0u);
                 umma_commit(p_empty);
-                if (hb == HB - 1) umma_commit(&kv_empty[kt & 1]);   // last reader of this K/V stage
+                if (hb == HB - 1) umma_commit(kv_empty);   // last reader of this key tile's K / V boxes
                 ++n;
             };
+            const uint32_t k_addr = smem_u32(sK);
             for (int kt = 0; kt < nkt; ++kt) {
-                mbar_wait(&kv_full[kt & 1], (kt >> 1) & 1);
+                // the single K/V stage is refilled only after the last P V of the previous key tile: flush it before waiting
+                if (pend_hb >= 0) { issue_pv(pend_hb, pend_kt); pend_hb = -1; }
+                mbar_wait(kv_full, kt & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(sK + (kt & 1) * ATC_BOX_BYTES);
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
                         if (u > 0) mbar_wait(s_free, (u - 1) & 1);
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             s_rel[ew_t] = kr; s_ts[ew_t] = kts; s_pad[ew_t] = kp;
         }
         nbar_sync<1, 256>();
-        int u = 0, n = 0, hist_cnt = 0;
+        int u = 0, n = 0;
         float pos_acc[HB];          // wide path only: sum of dS per head
 #pragma unroll
         for (int hb = 0; hb < HB; ++hb) pos_acc[hb] = 0.f;
@@ -714,30 +722,33 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                         atc_store_chunk_zero(sP, r, half, c);
                         atc_store_chunk_zero(sDS, r, half, c);
                     }
-                    // bias-table gradients: lane-private bins shared by the two chunk warps of a row block, which take turns
-                    if (!wide) {
-                        if (c == 0) {
-                            if (hist_cnt > 0) nbar_sync_dyn(6 + sub, 64);
-                        } else {
-                            nbar_sync_dyn(2 + sub, 64);
-                        }
-                        if (!masked_all[half]) {
+                    // bias-table gradients.  Bins are private to a ROW (two threads, the row's two chunks, share them through
+                    // shared-memory atomics); consecutive keys of a row mostly fall into the same log bucket, so runs are summed
+                    // in a register and only run ends touch shared memory - a handful of updates per 32 cells instead of a
+                    // chain of 32 dependent read-modify-writes.
+                    if (!masked_all[half]) {
+                        if (!wide) {
+                            unsigned prev = bk[half][0] & 31u;
+                            float acc = 0.f;
 #pragma unroll
                             for (int k = 0; k < 32; ++k) {
-                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 31u;   // masked cells (64) add an exact 0 to bin 0
-                                hist[bb * 128] += da[k];
+                                const unsigned bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 31u;   // masked cells (64) add an exact 0 to bin 0
+                                if (bb != prev) {
+                                    if (acc != 0.f) atomicAdd(hist + prev * 128, acc);
+                                    prev = bb;
+                                    acc = 0.f;
+                                }
+                                acc += da[k];
                             }
-                        }
-                        if (c == 0) nbar_arrive_dyn(2 + sub, 64);
-                        else nbar_arrive_dyn(6 + sub, 64);
-                        ++hist_cnt;
-                    } else if (!masked_all[half]) {
+                            if (acc != 0.f) atomicAdd(hist + prev * 128, acc);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                            if (da[k] != 0.f) {
-                                pos_acc[hb] += da[k];
-                                if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, da[k]);
+                            for (int k = 0; k < 32; ++k) {
+                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                                if (da[k] != 0.f) {
+                                    pos_acc[hb] += da[k];
+                                    if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, da[k]);
+                                }
                             }
                         }
                     }
@@ -750,7 +761,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             }
         }
         drain_dq(n - 1);
-        if (!wide && c == 0 && hist_cnt > 0) nbar_sync_dyn(6 + sub, 64);   // consume the partner's last hand-over
         // epilogue: dK / dV boxes [128 keys x 64] -> x silu'(z) -> bf16
         mbar_wait(dkdv_full, 0);
         tc_fence_after();

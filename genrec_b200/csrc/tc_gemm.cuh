@@ -526,6 +526,22 @@ struct TcEpiF32 {
         }
     }
 };
+// exp(x) to ~1 ulp with FMA-pipe arithmetic only (the library is compiled with --use_fast_math, which would turn expf into the
+// 2^-21-accurate ex2.approx path): Cody-Waite reduction x = n ln2 + r, |r| <= ln2 / 2, degree-6 polynomial, scale by 2^n.
+GRB_DEVINL float exp_accurate(float x) {
+    x = fminf(fmaxf(x, -87.f), 88.f);
+    const float n = rintf(x * 1.44269504088896341f);
+    float r = __fmaf_rn(n, -0.693145751953125f, x);            // ln2 high part (exact product for |n| < 2^10)
+    r = __fmaf_rn(n, -1.42860682030941723e-6f, r);             // ln2 low part
+    float p = 1.f / 720.f;
+    p = __fmaf_rn(p, r, 1.f / 120.f);
+    p = __fmaf_rn(p, r, 1.f / 24.f);
+    p = __fmaf_rn(p, r, 1.f / 6.f);
+    p = __fmaf_rn(p, r, 0.5f);
+    p = __fmaf_rn(p, r, 1.f);
+    p = __fmaf_rn(p, r, 1.f);
+    return p * __int_as_float(((int)n + 127) << 23);
+}
 // out = ACT(acc) -> fp32   (ACT 0: none, 1: silu) - the bias-free MLP layers of the RQ-VAE encoder (fp32-accurate split-bf16 GEMM)
 template <int ACT>
 struct TcEpiActF32 {
@@ -536,7 +552,7 @@ struct TcEpiActF32 {
     GRB_DEVINL void operator()(int, int, float (&v)[32], float (&)[32], int) const {
         if (ACT == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+            for (int i = 0; i < 32; ++i) v[i] = __fdiv_rn(v[i], 1.f + exp_accurate(-v[i]));
         }
     }
 };

@@ -12,12 +12,15 @@ Semantics = ``torch.optim.Adam(params, lr, betas, eps, weight_decay)`` followed 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from . import functional as Fn
+from ._lib import check, ptr, stream_ptr
 
 
 class FlatBuffers:
@@ -25,7 +28,9 @@ class FlatBuffers:
     ``param.data`` / ``param.grad`` re-homed as a view (256-byte aligned slots).  Works on CPU tensors too, which is how the
     world_size-2 gloo tests exercise the data-parallel plumbing without a GPU."""
 
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, alloc=None, pad_to: int = 64):
+        """alloc(n, dtype) -> zeroed 1-D tensor (default torch.zeros on the parameters' device); pad_to: the total length is
+        rounded up to a multiple of it (the peer-memory optimizer needs 8 * world)."""
         params = [p for p in model.parameters() if p.requires_grad]
         assert params, "no trainable parameters"
         dev = params[0].device
@@ -33,10 +38,13 @@ class FlatBuffers:
         for p in params:
             offs.append(n)
             n += (p.numel() + 63) // 64 * 64          # 256-byte aligned slots (bf16 views stay 16-byte aligned)
+        n = (n + pad_to - 1) // pad_to * pad_to
         self.n, self.offsets, self.params, self.device = n, offs, params, dev
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.mirror = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        if alloc is None:
+            alloc = lambda k, dt: torch.zeros(k, dtype=dt, device=dev)  # noqa: E731
+        self.flat = alloc(n, torch.float32)
+        self.grad = alloc(n, torch.float32)
+        self.mirror = alloc(n, torch.bfloat16)
         self._mirror_view, self._grad_view = {}, {}
         with torch.no_grad():
             for p, o in zip(params, offs):
@@ -67,16 +75,73 @@ def allreduce_gradients(buffers: FlatBuffers, group=None) -> float:
     return 1.0 / w
 
 
+class PeerMemory:
+    """Symmetric (peer-mapped, multicast-mapped where the fabric supports it) allocations for the one-pass data-parallel optimizer
+    step ``grb_dp_adam_step`` (csrc/dp_adam.cuh).  Built on ``torch.distributed._symmetric_memory`` for the rendezvous only -
+    the collective itself is our kernel.  Raises if symmetric memory is unavailable; FlatAdam then keeps the NCCL all-reduce."""
+
+    def __init__(self, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm, self.device = symm, device
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.handles = {}
+        self.tensors = []
+
+    def alloc(self, n: int, dtype) -> torch.Tensor:
+        t = self.symm.empty(n, dtype=dtype, device=self.device)
+        h = self.symm.rendezvous(t, self.group.group_name)
+        t.zero_()
+        self.handles[t.data_ptr()] = h
+        self.tensors.append(t)
+        return t
+
+    def handle(self, t: torch.Tensor):
+        return self.handles[t.data_ptr()]
+
+    def peer_ptrs(self, t: torch.Tensor) -> torch.Tensor:
+        return torch.tensor([int(x) for x in self.handle(t).buffer_ptrs], dtype=torch.int64, device=self.device)
+
+    def multicast_ptr(self, t: torch.Tensor) -> int:
+        h = self.handle(t)
+        try:
+            return int(h.multicast_ptr) if h.has_multicast_support(self.device.type, self.device.index) or int(h.multicast_ptr) else 0
+        except Exception:  # noqa: BLE001
+            return int(getattr(h, "multicast_ptr", 0) or 0)
+
+
 class FlatAdam:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True, unit_loss_grad: bool = False):
+                 weight_decay: float = 0.0, process_group=None, grad_sink: bool = True, unit_loss_grad: bool = False,
+                 peer_memory: Optional[bool] = None):
         """``unit_loss_grad=True`` promises that every training forward is followed by exactly one ``loss.backward()`` with
         gradient 1 (no loss scaling, no gradient accumulation through a scaled loss): the fused head then accumulates its
         parameter gradients into the flat buffer in the same pass that computes the loss.  The promise is checked on the
         device (``grb_assert_unit_scalar``).  Default False: fully general, a few microseconds slower per step."""
-        self.buffers = FlatBuffers(model)
+        dev0 = next(p for p in model.parameters() if p.requires_grad).device
+        assert dev0.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
+        # data-parallel step: one pass over NVLink peer memory (multimem reduce + Adam + multicast parameter store, csrc/dp_adam.cuh)
+        # when symmetric memory can be set up, otherwise NCCL all-reduce + the local fused Adam.  GRB_DP=nccl forces the latter.
+        self.peer = None
+        self.dp_mode = "single"
+        w = world_size(process_group)
+        want_peer = (os.environ.get("GRB_DP", "") != "nccl") if peer_memory is None else bool(peer_memory)
+        if w > 1:
+            self.dp_mode = "nccl-allreduce"
+            if want_peer:
+                try:
+                    self.peer = PeerMemory(dev0, process_group)
+                    self.buffers = FlatBuffers(model, alloc=self.peer.alloc, pad_to=64 * w)
+                    self._peer_setup()
+                    self.dp_mode = "peer-multimem" if self._mc[0] else "peer-p2p"
+                except Exception as e:  # noqa: BLE001
+                    if peer_memory:
+                        raise
+                    self.peer = None
+                    self._peer_error = f"{type(e).__name__}: {e}"
+        if self.peer is None:
+            self.buffers = FlatBuffers(model)
         dev = self.buffers.device
-        assert dev.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
         self.model, self.lr, self.betas, self.eps, self.weight_decay = model, lr, betas, eps, weight_decay
         self.group = process_group
         self.n, self.flat, self.grad, self.mirror, self.params = (self.buffers.n, self.buffers.flat, self.buffers.grad,
@@ -106,8 +171,30 @@ class FlatAdam:
     def world(self) -> int:
         return world_size(self.group)
 
+    def _peer_setup(self) -> None:
+        pm, b = self.peer, self.buffers
+        self._sig = pm.alloc(2 * pm.world, torch.int32)
+        self._epoch = torch.zeros(2, dtype=torch.int32, device=b.device)
+        self._peer_ptrs = tuple(pm.peer_ptrs(t) for t in (b.grad, b.flat, b.mirror, self._sig))
+        self._mc = tuple(pm.multicast_ptr(t) for t in (b.grad, b.flat, b.mirror))
+        if not all(self._mc):
+            self._mc = (0, 0, 0)
+        torch.cuda.synchronize(b.device)
+        dist.barrier(pm.group)
+
     def step(self) -> None:
-        """all-reduce(SUM) -> fused Adam with grad_scale = 1/world -> mirror refresh -> grad zeroed."""
+        """world == 1: fused Adam.  world > 1: reduce + Adam + parameter broadcast in one pass over peer memory (dp_mode "peer-*"),
+        or all-reduce(SUM) -> fused Adam with grad_scale = 1/world (dp_mode "nccl-allreduce"); either way the bf16 mirror is
+        refreshed and the flat gradient is zero afterwards."""
+        if self.peer is not None:
+            pg, pp, pmir, psig = self._peer_ptrs
+            with torch.cuda.device(self.flat.device):
+                check(_lib.load().grb_dp_adam_step(
+                    ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.mirror), self._mc[0] or None, self._mc[1] or None,
+                    self._mc[2] or None, ptr(pg), ptr(pp), ptr(pmir), ptr(psig), ptr(self._sig), ptr(self._epoch), self.n, self.peer.rank,
+                    self.peer.world, ptr(self.state), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                    1.0 / self.peer.world, stream_ptr(self.flat.device)))
+            return
         scale = allreduce_gradients(self.buffers, self.group)
         Fn.adam_step(self.flat, self.grad, self.m, self.v, self.mirror, self.state, self.lr, self.betas[0], self.betas[1],
                      self.eps, self.weight_decay, scale, True)
@@ -122,7 +209,13 @@ class FlatAdam:
 
     def state_dict(self) -> dict:
         """Adam moments + step state (``torch.optim.Adam``-style checkpointing; parameters live in ``model.state_dict()``)."""
-        return {"m": self.m.clone(), "v": self.v.clone(), "state": self.state.clone(),
+        m, v = self.m.clone(), self.v.clone()
+        if self.peer is not None:     # each rank holds the moments of its own slice only: assemble the full vectors
+            per = self.n // self.peer.world
+            lo = self.peer.rank * per
+            dist.all_gather_into_tensor(m, self.m[lo:lo + per].clone(), group=self.peer.group)
+            dist.all_gather_into_tensor(v, self.v[lo:lo + per].clone(), group=self.peer.group)
+        return {"m": m, "v": v, "state": self.state.clone(),
                 "hyper": dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay), "n": self.n}
 
     def load_state_dict(self, sd: dict) -> None:

@@ -205,6 +205,19 @@ int grb_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, size_t n
  * gradient of the loss is known. */
 int grb_assert_unit_scalar(const float* value, void* stream);
 
+/* Data-parallel optimizer step over NVLink peer memory, replacing `all_reduce(grad)` + Adam (the DDP gradient all-reduce of
+ * accelerator.backward, genrec/trainers/hstu_trainer.py:159, + optimizer.step, :160): cross-GPU barrier, then each rank reduces ITS
+ * slice of the flat gradient over all ranks (multimem.ld_reduce through the NVSwitch when mc_* are given, peer loads otherwise),
+ * applies Adam to the slice and stores the new fp32 parameters and their bf16 mirror to every rank (multimem.st / peer stores),
+ * barrier, gradient zeroed.  All buffers are symmetric allocations of n elements, n % (8 * world) == 0.
+ *   peer_g / peer_p / peer_mirror / peer_sig: DEVICE arrays of `world` pointers (rank order) ; mc_*: multicast addresses or NULL
+ *   sig: this rank's flag words [2][world] (zero-initialised symmetric memory) ; epoch: 2 local counters (zero-initialised)
+ *   state: as grb_adam_step (ticked here).  grad_scale = 1/world reproduces DDP's gradient averaging. */
+int grb_dp_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, const void* mc_g, void* mc_p, void* mc_p_bf16,
+                     const void* peer_g, const void* peer_p, const void* peer_p_bf16, const void* peer_sig, void* sig, void* epoch,
+                     size_t n, int rank, int world, float* state, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ RQ-VAE residual argmin
  * Replaces the Quantize.forward distance+argmin (genrec/models/rqvae.py:185-199, eval branch :246-248) iterated by
  * RqVae.get_semantic_ids (:397-412).  x [N, D] fp32 latent, codebooks [levels, K, D] fp32.

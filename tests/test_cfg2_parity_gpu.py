@@ -61,7 +61,11 @@ def test_cfg2_full_model_vs_oracle():
     # ours
     m = m.to(dev).train()
     got = {}
-    hook = m.layers[NB - 1].register_forward_pre_hook(lambda mod, args: args[0].register_hook(lambda g: got.__setitem__("dx_last", g.clone())))
+    def grab(mod, args):
+        args[0].register_hook(lambda g: got.__setitem__("dx_last", g.clone()))
+        return None
+
+    hook = m.layers[NB - 1].register_forward_pre_hook(grab)
     _, loss = m(ids.to(dev), ts.to(dev), tg.to(dev))
     loss.backward()
     hook.remove()
