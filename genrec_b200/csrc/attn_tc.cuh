@@ -139,7 +139,7 @@ GRB_DEVINL void atc_buckets(uint32_t (&bk)[8], int i, int j0, int ri, long long 
                     b = e + (a >= s_thr32[e + 1] ? 1 : 0);
                     if (clamp) b = b < ntm1 ? b : ntm1;
                 } else {
-                    b = time_bucket_dev(ti - s_ts[k], s_thr64, ntime);
+                    b = time_bucket_dev(ti - ((j0 + k < L) ? s_ts[k] : 0ll), s_thr64, ntime);
                 }
             }
             if (MASKED) {
@@ -455,13 +455,11 @@ struct AtcBwdSmem {
     static constexpr int kDO = kQ + 2 * ATC_BOX_BYTES;             // [2 stages]
     static constexpr int kP = kDO + 2 * ATC_BOX_BYTES;
     static constexpr int kDS = kP + ATC_TILE2_BYTES;
-    static constexpr int kHist = kDS + ATC_TILE2_BYTES;            // [HB][32 bins][128 rows] fp32
-    static constexpr int kRel = kHist + HB * 32 * 128 * 4;
-    static constexpr int kTs = kRel + 128 * 4;
-    static constexpr int kPad = kTs + 128 * 8;
+    static constexpr int kHist = kDS + ATC_TILE2_BYTES;            // [HB][32 bins][256 element-wise threads] fp32: private bins
+    static constexpr int kRel = kHist + HB * 32 * 256 * 4;
+    static constexpr int kPad = kRel + 128 * 4;
     static constexpr int kThr32 = kPad + 128;
-    static constexpr int kThr64 = kThr32 + 36 * 4;
-    static constexpr int kTbl = kThr64 + 66 * 8;
+    static constexpr int kTbl = kThr32 + 36 * 4;
     static constexpr int kBars = kTbl + HB * ATC_TBL_LD * 4;
     static constexpr int kBytes = kBars + 20 * 8 + 16;
 };
@@ -481,12 +479,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     unsigned char* sDS = base + SM::kDS;
     float* s_hist = reinterpret_cast<float*>(base + SM::kHist);
     int* s_rel = reinterpret_cast<int*>(base + SM::kRel);
-    long long* s_ts = reinterpret_cast<long long*>(base + SM::kTs);
     uint8_t* s_pad = base + SM::kPad;
     uint32_t* s_thr32 = reinterpret_cast<uint32_t*>(base + SM::kThr32);
-    long long* s_thr64 = reinterpret_cast<long long*>(base + SM::kThr64);
     float* s_tbl = reinterpret_cast<float*>(base + SM::kTbl);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::kBars);
+    // the 64-bit (wide) path reads the key timestamps and the thresholds straight from global memory: rare, and shared memory
+    // is needed for the private histogram bins
+    const long long* s_thr64 = a.thr64;
     uint64_t* kv_full = bars;            // TMA -> MMA
     uint64_t* qdo_full = bars + 1;       // [2]
     uint64_t* qdo_empty = bars + 3;      // [2]
@@ -508,6 +507,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     const int L = a.L;
     const int k0 = kt * 128;
     const long long tok0 = (long long)b * L;
+    const long long* s_ts = a.ts != nullptr ? a.ts + tok0 + k0 : nullptr;     // key timestamps of this tile (wide path only, guarded by j < L)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmP);
@@ -617,18 +617,16 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         const int ntime = has_time ? a.ntime : 0;
         const bool wide = has_time && a.wide[b] != 0;
         for (int k = ew_t; k < 36; k += 256) s_thr32[k] = k <= 31 ? (uint32_t)a.thr64[k] : 0xffffffffu;
-        for (int k = ew_t; k < 65; k += 256) s_thr64[k] = a.thr64[k];
         for (int hb = 0; hb < HB; ++hb) atc_build_table(s_tbl + hb * ATC_TBL_LD, a, box * HB + hb, ew_t, 256);
-        for (int k = ew_t; k < HB * 32 * 128; k += 256) s_hist[k] = 0.f;
+        for (int k = ew_t; k < HB * 32 * 256; k += 256) s_hist[k] = 0.f;
         if (ew_t < 128) {
             const int j = k0 + ew_t;
-            int kr = 0; long long kts = 0; uint8_t kp = 1;
+            int kr = 0; uint8_t kp = 1;
             if (j < L) {
                 kp = a.pad[tok0 + j];
                 if (has_time && !wide) kr = a.rel32[tok0 + j];
-                if (wide) kts = a.ts[tok0 + j];
             }
-            s_rel[ew_t] = kr; s_ts[ew_t] = kts; s_pad[ew_t] = kp;
+            s_rel[ew_t] = kr; s_pad[ew_t] = kp;
         }
         nbar_sync<1, 256>();
         int u = 0, n = 0;
@@ -691,7 +689,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb) {
                 const float* tbl = s_tbl + hb * ATC_TBL_LD;
-                float* hist = s_hist + hb * 32 * 128 + r;
+                float* hist = s_hist + hb * 32 * 256 + ew_t;     // this thread's private column of bins
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(sda_full, u & 1);
@@ -722,10 +720,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                         atc_store_chunk_zero(sP, r, half, c);
                         atc_store_chunk_zero(sDS, r, half, c);
                     }
-                    // bias-table gradients.  Bins are private to a ROW (two threads, the row's two chunks, share them through
-                    // shared-memory atomics); consecutive keys of a row mostly fall into the same log bucket, so runs are summed
-                    // in a register and only run ends touch shared memory - a handful of updates per 32 cells instead of a
-                    // chain of 32 dependent read-modify-writes.
+                    // bias-table gradients.  Every element-wise thread owns a private column of 32 bins per head in shared memory
+                    // (plain read-modify-write, bank-conflict free, no atomics).  Consecutive keys of a row mostly fall into the
+                    // same log bucket, so runs are summed in a register and only run ends touch shared memory - a handful of
+                    // updates per 32 cells instead of a chain of 32 dependent read-modify-writes.
                     if (!masked_all[half]) {
                         if (!wide) {
                             unsigned prev = bk[half][0] & 31u;
@@ -734,13 +732,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                             for (int k = 0; k < 32; ++k) {
                                 const unsigned bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 31u;   // masked cells (64) add an exact 0 to bin 0
                                 if (bb != prev) {
-                                    if (acc != 0.f) atomicAdd(hist + prev * 128, acc);
+                                    hist[prev * 256] += acc;
                                     prev = bb;
                                     acc = 0.f;
                                 }
                                 acc += da[k];
                             }
-                            if (acc != 0.f) atomicAdd(hist + prev * 128, acc);
+                            hist[prev * 256] += acc;
                         } else {
 #pragma unroll
                             for (int k = 0; k < 32; ++k) {
@@ -794,8 +792,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             const int ew_warp = warp - 2;
             for (int e = ew_warp; e < HB * 32; e += ATC_EW_WARPS) {
                 const int hb = e >> 5, v = e & 31;
-                const float* row = s_hist + (size_t)e * 128;
-                float sum = row[lane] + row[lane + 32] + row[lane + 64] + row[lane + 96];
+                const float* row = s_hist + (size_t)e * 256;
+                float sum = row[lane] + row[lane + 32] + row[lane + 64] + row[lane + 96] + row[lane + 128] + row[lane + 160] +
+                            row[lane + 192] + row[lane + 224];
                 sum = warp_sum(sum);
                 if (lane == 0 && sum != 0.f) {
                     const int h = box * HB + hb;
