@@ -77,6 +77,22 @@ template <int ID, int N>
 GRB_DEVINL void nbar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 GRB_DEVINL void nbar_sync_dyn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 GRB_DEVINL void nbar_arrive_dyn(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// mbarrier wait with a suspend-time hint: a waiting warp sleeps in hardware instead of re-polling (the polls of 8 element-wise
+// warps and of the TMA lane would otherwise take issue slots from the CTA that shares the SM).  Not for the MMA lane: it is the
+// one consumer whose wake-up latency is on the critical path.
+GRB_DEVINL void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_S:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE_S;\n"
+        "bra WAIT_LOOP_S;\n"
+        "WAIT_DONE_S:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
 GRB_DEVINL uint64_t atc_kmaj(uint32_t addr) { return umma_desc(addr, 16, 1024); }          // K-major box (rows of 128 B)
 GRB_DEVINL uint64_t atc_mnmaj(uint32_t addr) { return umma_desc(addr, ATC_BOX_BYTES, 1024); }  // MN-major, next 64-wide block one box away
 
@@ -113,34 +129,31 @@ __global__ void __launch_bounds__(256) hstu_seq_prep_kernel(const long long* __r
 // ------------------------------------------------------------------------------------------------ bucket bytes of 32 cells
 // cells (row i, keys j0 .. j0+31) ; bk[k >> 2] byte (k & 3) = time bucket of cell k, or 64 when the cell is masked.
 // s_rel / s_ts / s_pad point at the first of the 32 keys in shared memory.
-template <bool WIDE, bool MASKED>
-GRB_DEVINL void atc_buckets(uint32_t (&bk)[8], int i, int j0, int ri, long long ti, const int* s_rel, const long long* s_ts,
-                            const uint8_t* s_pad, const uint32_t* s_thr32, const long long* s_thr64, int ntime, int L, bool row_ok) {
+struct AtcBk8 {
+    uint32_t w[8];
+};
+// 32-bit path (the sequence spans < 2^31 ticks): inlined, this is the hot one
+template <bool MASKED>
+GRB_DEVINL void atc_buckets_narrow(uint32_t (&bk)[8], int i, int j0, int ri, const int* s_rel, const uint8_t* s_pad, const uint32_t* s_thr32,
+                                   int ntime, int L, bool row_ok) {
     const int ntm1 = ntime - 1;
     const bool clamp = ntm1 < 31;     // 32-bit differences never reach bucket 32 (warp-uniform)
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         uint32_t word = 0;
-        int rj[4] = {0, 0, 0, 0};
-        if (!WIDE) {
-            const int4 r4 = *reinterpret_cast<const int4*>(s_rel + 4 * w);      // four keys per broadcast LDS.128
-            rj[0] = r4.x; rj[1] = r4.y; rj[2] = r4.z; rj[3] = r4.w;
-        }
+        const int4 r4 = *reinterpret_cast<const int4*>(s_rel + 4 * w);      // four keys per broadcast LDS.128
+        const int rj[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = w * 4 + q;
             int b = 0;
             if (ntime > 0) {
-                if (!WIDE) {
-                    // e = floor(log2 |d|) (-1 for d == 0: thr32[0] == 0 then gives bucket 0) ; bucket = e + (|d| >= thr[e + 1])
-                    const int d = ri - rj[q];
-                    const unsigned a = (unsigned)(d < 0 ? -d : d);
-                    const int e = 31 - __clz(a);
-                    b = e + (a >= s_thr32[e + 1] ? 1 : 0);
-                    if (clamp) b = b < ntm1 ? b : ntm1;
-                } else {
-                    b = time_bucket_dev(ti - ((j0 + k < L) ? s_ts[k] : 0ll), s_thr64, ntime);
-                }
+                // e = floor(log2 |d|) (-1 for d == 0: thr32[0] == 0 then gives bucket 0) ; bucket = e + (|d| >= thr[e + 1])
+                const int d = ri - rj[q];
+                const unsigned a = (unsigned)(d < 0 ? -d : d);
+                const int e = 31 - __clz(a);
+                b = e + (a >= s_thr32[e + 1] ? 1 : 0);
+                if (clamp) b = b < ntm1 ? b : ntm1;
             }
             if (MASKED) {
                 const int j = j0 + k;
@@ -152,6 +165,31 @@ GRB_DEVINL void atc_buckets(uint32_t (&bk)[8], int i, int j0, int ri, long long 
         bk[w] = word;
     }
 }
+// 64-bit path: a sequence that spans >= 2^31 ticks (millisecond clocks, synthetic extremes).  Out of line on purpose: it is
+// rare and its 64-bit arithmetic would otherwise be inlined at every call site (instruction-cache footprint of the hot loop).
+// g_ts points at the timestamps of the 32 keys in GLOBAL memory.
+__device__ __noinline__ AtcBk8 atc_buckets_wide(int i, int j0, long long ti, const long long* g_ts, const uint8_t* s_pad,
+                                                const long long* thr64, int ntime, int L, int row_ok) {
+    AtcBk8 out;
+    for (int w = 0; w < 8; ++w) {
+        uint32_t word = 0;
+        for (int q = 0; q < 4; ++q) {
+            const int k = w * 4 + q;
+            const int j = j0 + k;
+            int b = 0;
+            if (ntime > 0 && j < L) b = time_bucket_dev(ti - g_ts[k], thr64, ntime);
+            const bool valid = row_ok && j <= i && j < L && s_pad[k] == 0;
+            b = valid ? b : 64;
+            word |= (uint32_t)b << (8 * q);
+        }
+        out.w[w] = word;
+    }
+    return out;
+}
+// bucket bytes of one (row, 32-key chunk): classification -> all masked / narrow fast / narrow masked / wide
+GRB_DEVINL bool atc_chunk_buckets(uint32_t (&bk)[8], int q_first, int lane, int i, int j0, int ri, long long ti, bool wide, const int* s_rel,
+                                  const long long* g_ts, const uint8_t* s_pad, const uint32_t* s_thr32, const long long* thr64, int ntime, int L,
+                                  bool row_ok);
 GRB_DEVINL void atc_buckets_all_masked(uint32_t (&bk)[8]) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) bk[w] = 0x40404040u;
@@ -196,6 +234,24 @@ GRB_DEVINL AtcChunkClass atc_classify(int q_first, int k_first, int L, const uin
     return cc;
 }
 
+GRB_DEVINL bool atc_chunk_buckets(uint32_t (&bk)[8], int q_first, int lane, int i, int j0, int ri, long long ti, bool wide, const int* s_rel,
+                                  const long long* g_ts, const uint8_t* s_pad, const uint32_t* s_thr32, const long long* thr64, int ntime, int L,
+                                  bool row_ok) {
+    const AtcChunkClass cl = atc_classify(q_first, j0, L, s_pad, lane);
+    if (cl.all_masked) {
+        atc_buckets_all_masked(bk);
+    } else if (wide) {
+        const AtcBk8 r = atc_buckets_wide(i, j0, ti, g_ts, s_pad, thr64, ntime, L, row_ok ? 1 : 0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) bk[w] = r.w[w];
+    } else if (cl.needs_mask) {
+        atc_buckets_narrow<true>(bk, i, j0, ri, s_rel, s_pad, s_thr32, ntime, L, row_ok);
+    } else {
+        atc_buckets_narrow<false>(bk, i, j0, ri, s_rel, s_pad, s_thr32, ntime, L, row_ok);
+    }
+    return cl.all_masked;
+}
+
 // ================================================================================================ forward
 template <int DH>
 struct AtcFwdSmem {
@@ -205,13 +261,11 @@ struct AtcFwdSmem {
     static constexpr int kV = kK + ATC_BOX_BYTES;
     static constexpr int kP = kV + ATC_BOX_BYTES;
     static constexpr int kSmall = kP + ATC_TILE2_BYTES;
-    // small area: rel[2][128] int | ts[2][128] ll | pad[2][128] | thr32[36] | thr64[65] | tbl[HB][ATC_TBL_LD] | barriers
+    // small area: rel[2][128] int | pad[2][128] | thr32[36] | tbl[HB][ATC_TBL_LD] | barriers
     static constexpr int kRel = kSmall;
-    static constexpr int kTs = kRel + 2 * 128 * 4;
-    static constexpr int kPad = kTs + 2 * 128 * 8;
+    static constexpr int kPad = kRel + 2 * 128 * 4;
     static constexpr int kThr32 = kPad + 2 * 128;
-    static constexpr int kThr64 = kThr32 + 36 * 4;
-    static constexpr int kTbl = kThr64 + 66 * 8;
+    static constexpr int kTbl = kThr32 + 36 * 4;
     static constexpr int kBars = kTbl + HB * ATC_TBL_LD * 4;
     static constexpr int kBytes = kBars + 16 * 8 + 16;
 };
@@ -221,16 +275,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
     using SM = AtcFwdSmem<DH>;
     constexpr int HB = SM::HB, KS = DH / 16;
     extern __shared__ unsigned char atc_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(atc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = atc_smem_raw + ((1024u - (smem_u32(atc_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     unsigned char* sQ = base + SM::kQ;
     unsigned char* sK = base + SM::kK;
     unsigned char* sV = base + SM::kV;
     unsigned char* sP = base + SM::kP;
     int* s_rel = reinterpret_cast<int*>(base + SM::kRel);
-    long long* s_ts = reinterpret_cast<long long*>(base + SM::kTs);
     uint8_t* s_pad = base + SM::kPad;
     uint32_t* s_thr32 = reinterpret_cast<uint32_t*>(base + SM::kThr32);
-    long long* s_thr64 = reinterpret_cast<long long*>(base + SM::kThr64);
     float* s_tbl = reinterpret_cast<float*>(base + SM::kTbl);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::kBars);
     uint64_t* q_full = bars;            // TMA -> MMA
@@ -282,7 +334,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             mbar_expect_tx(q_full, ATC_BOX_BYTES);
             tma_load_2d(sQ, &tmP, 2 * a.D + box * 64, row_q, q_full);
             for (int kt = 0; kt < nkt; ++kt) {
-                mbar_wait(kv_empty, (kt & 1) ^ 1);
+                mbar_wait_sleep(kv_empty, (kt & 1) ^ 1);
                 mbar_expect_tx(kv_full, 2 * ATC_BOX_BYTES);
                 tma_load_2d(sK, &tmP, 3 * a.D + box * 64, (int)tok0 + kt * 128, kv_full);
                 tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + kt * 128, kv_full);
@@ -345,25 +397,23 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
         const bool wide = has_time && a.wide[b] != 0;
         // thresholds + bias tables
         for (int k = ew_t; k < 36; k += 256) s_thr32[k] = k <= 31 ? (uint32_t)a.thr64[k] : 0xffffffffu;
-        for (int k = ew_t; k < 65; k += 256) s_thr64[k] = a.thr64[k];
         for (int hb = 0; hb < HB; ++hb) atc_build_table(s_tbl + hb * ATC_TBL_LD, a, box * HB + hb, ew_t, 256);
+        const long long* g_ts = a.ts != nullptr ? a.ts + tok0 : nullptr;      // wide path reads key timestamps from global memory
         const int ri = (has_time && !wide && row_ok) ? a.rel32[tok0 + i] : 0;
         const long long ti = (wide && row_ok) ? a.ts[tok0 + i] : 0;
         // key metadata of tile kt -> buffer kt & 1 (thread k < 128 stages key k)
-        int k_rel = 0; long long k_ts = 0; uint8_t k_pad = 1;
+        int k_rel = 0; uint8_t k_pad = 1;
         auto fetch_keys = [&](int kt) {
             const int j = kt * 128 + ew_t;
-            k_rel = 0; k_ts = 0; k_pad = 1;
+            k_rel = 0; k_pad = 1;
             if (ew_t < 128 && j < L) {
                 k_pad = a.pad[tok0 + j];
                 if (has_time && !wide) k_rel = a.rel32[tok0 + j];
-                if (wide) k_ts = a.ts[tok0 + j];
             }
         };
         auto stage_keys = [&](int kt) {
             if (ew_t < 128) {
                 s_rel[(kt & 1) * 128 + ew_t] = k_rel;
-                s_ts[(kt & 1) * 128 + ew_t] = k_ts;
                 s_pad[(kt & 1) * 128 + ew_t] = k_pad;
             }
         };
@@ -381,22 +431,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
-                const AtcChunkClass cl = atc_classify(q0 + sub * 32, k0 + cc0, L, s_pad + kb + cc0, lane);
-                masked_all[half] = cl.all_masked;
-                if (cl.all_masked) atc_buckets_all_masked(bk[half]);
-                else if (wide) {
-                    if (cl.needs_mask) atc_buckets<true, true>(bk[half], i, k0 + cc0, ri, ti, s_rel + kb + cc0, s_ts + kb + cc0, s_pad + kb + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                    else atc_buckets<true, false>(bk[half], i, k0 + cc0, ri, ti, s_rel + kb + cc0, s_ts + kb + cc0, s_pad + kb + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                } else {
-                    if (cl.needs_mask) atc_buckets<false, true>(bk[half], i, k0 + cc0, ri, ti, s_rel + kb + cc0, s_ts + kb + cc0, s_pad + kb + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                    else atc_buckets<false, false>(bk[half], i, k0 + cc0, ri, ti, s_rel + kb + cc0, s_ts + kb + cc0, s_pad + kb + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                }
+                masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + kb + cc0,
+                                                     g_ts + k0 + cc0, s_pad + kb + cc0, s_thr32, a.thr64, ntime, L, row_ok);
             }
             for (int hb = 0; hb < HB; ++hb) {
                 const float* tbl = s_tbl + hb * ATC_TBL_LD;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    mbar_wait(s_full, u & 1);
+                    mbar_wait_sleep(s_full, u & 1);
                     tc_fence_after();
                     float s[32];
                     if (!masked_all[half]) {
@@ -407,7 +449,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_free);
                     ++u;
-                    if (half == 0 && n > 0) mbar_wait(p_empty, (n - 1) & 1);   // P V of the previous head has read the P tile
+                    if (half == 0 && n > 0) mbar_wait_sleep(p_empty, (n - 1) & 1);   // P V of the previous head has read the P tile
                     if (!masked_all[half]) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
@@ -430,7 +472,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             }
         }
         // epilogue: O box [128 x 64] fp32 in TMEM -> bf16 rows
-        mbar_wait(o_full, 0);
+        mbar_wait_sleep(o_full, 0);
         tc_fence_after();
         float o[32];
         tmem_ld32_nowait(tm_O + ((uint32_t)(sub * 32) << 16) + c * 32, o);
@@ -470,7 +512,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     using SM = AtcBwdSmem<DH>;
     constexpr int HB = SM::HB, KS = DH / 16;
     extern __shared__ unsigned char atc_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(atc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = atc_smem_raw + ((1024u - (smem_u32(atc_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     unsigned char* sK = base + SM::kK;
     unsigned char* sV = base + SM::kV;
     unsigned char* sQ = base + SM::kQ;
@@ -485,7 +527,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::kBars);
     // the 64-bit (wide) path reads the key timestamps and the thresholds straight from global memory: rare, and shared memory
     // is needed for the private histogram bins
-    const long long* s_thr64 = a.thr64;
     uint64_t* kv_full = bars;            // TMA -> MMA
     uint64_t* qdo_full = bars + 1;       // [2]
     uint64_t* qdo_empty = bars + 3;      // [2]
@@ -540,7 +581,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + k0, kv_full);
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_wait_sleep(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[st], 2 * ATC_BOX_BYTES);
                 tma_load_2d(sQ + st * ATC_BOX_BYTES, &tmP, 2 * a.D + box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
                 tma_load_2d(sDO + st * ATC_BOX_BYTES, &tmDO, box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
@@ -638,7 +679,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             const int buf = m & 1;
             const int m_it = m / HB, m_hb = m % HB;
             const int qi = (kt + m_it) * 128 + r;
-            mbar_wait(&dq_full[buf], (m >> 1) & 1);
+            mbar_wait_sleep(&dq_full[buf], (m >> 1) & 1);
             tc_fence_after();
             constexpr int W = DH / 2;     // columns per thread
             float v[W];
@@ -675,16 +716,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
-                const AtcChunkClass cl = atc_classify(q0 + sub * 32, k0 + cc0, L, s_pad + cc0, lane);
-                masked_all[half] = cl.all_masked;
-                if (cl.all_masked) atc_buckets_all_masked(bk[half]);
-                else if (wide) {
-                    if (cl.needs_mask) atc_buckets<true, true>(bk[half], i, k0 + cc0, ri, ti, s_rel + cc0, s_ts + cc0, s_pad + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                    else atc_buckets<true, false>(bk[half], i, k0 + cc0, ri, ti, s_rel + cc0, s_ts + cc0, s_pad + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                } else {
-                    if (cl.needs_mask) atc_buckets<false, true>(bk[half], i, k0 + cc0, ri, ti, s_rel + cc0, s_ts + cc0, s_pad + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                    else atc_buckets<false, false>(bk[half], i, k0 + cc0, ri, ti, s_rel + cc0, s_ts + cc0, s_pad + cc0, s_thr32, s_thr64, ntime, L, row_ok);
-                }
+                masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + cc0, s_ts + cc0, s_pad + cc0,
+                                                     s_thr32, a.thr64, ntime, L, row_ok);
             }
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb) {
@@ -692,7 +725,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 float* hist = s_hist + hb * 32 * 256 + ew_t;     // this thread's private column of bins
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    mbar_wait(sda_full, u & 1);
+                    mbar_wait_sleep(sda_full, u & 1);
                     tc_fence_after();
                     float s[32], da[32];
                     if (!masked_all[half]) {
@@ -704,7 +737,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sda_free);
                     ++u;
-                    if (half == 0 && n > 0) mbar_wait(pds_empty, (n - 1) & 1);
+                    if (half == 0 && n > 0) mbar_wait_sleep(pds_empty, (n - 1) & 1);
                     if (!masked_all[half]) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
@@ -760,7 +793,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         }
         drain_dq(n - 1);
         // epilogue: dK / dV boxes [128 keys x 64] -> x silu'(z) -> bf16
-        mbar_wait(dkdv_full, 0);
+        mbar_wait_sleep(dkdv_full, 0);
         tc_fence_after();
         {
             const int j = k0 + r;
@@ -845,11 +878,9 @@ __global__ void __launch_bounds__(256) hstu_dq_finish_kernel(const float* __rest
 // classification, same fast / masked / wide variants).  grid (ceil(L / 32), ceil(L / 128), B), block 128.
 __global__ void __launch_bounds__(128) hstu_bucket_bytes_debug_kernel(HstuTcArgs a, uint8_t* __restrict__ out) {
     pdl_wait();
-    __shared__ int s_rel[32];
-    __shared__ long long s_ts[32];
+    __shared__ __align__(16) int s_rel[32];
     __shared__ uint8_t s_pad[32];
     __shared__ uint32_t s_thr32[36];
-    __shared__ long long s_thr64[66];
     const int b = blockIdx.z, q0 = blockIdx.y * 128, j0 = blockIdx.x * 32;
     const int L = a.L, t = threadIdx.x, sub = t >> 5, lane = t & 31;
     const long long tok0 = (long long)b * L;
@@ -857,16 +888,14 @@ __global__ void __launch_bounds__(128) hstu_bucket_bytes_debug_kernel(HstuTcArgs
     const int ntime = has_time ? a.ntime : 0;
     const bool wide = has_time && a.wide[b] != 0;
     for (int k = t; k < 36; k += 128) s_thr32[k] = k <= 31 ? (uint32_t)a.thr64[k] : 0xffffffffu;
-    for (int k = t; k < 65; k += 128) s_thr64[k] = a.thr64[k];
     if (t < 32) {
         const int j = j0 + t;
-        int kr = 0; long long kts = 0; uint8_t kp = 1;
+        int kr = 0; uint8_t kp = 1;
         if (j < L) {
             kp = a.pad[tok0 + j];
             if (has_time && !wide) kr = a.rel32[tok0 + j];
-            if (wide) kts = a.ts[tok0 + j];
         }
-        s_rel[t] = kr; s_ts[t] = kts; s_pad[t] = kp;
+        s_rel[t] = kr; s_pad[t] = kp;
     }
     __syncthreads();
     const int i = q0 + t;
@@ -874,15 +903,8 @@ __global__ void __launch_bounds__(128) hstu_bucket_bytes_debug_kernel(HstuTcArgs
     const int ri = (has_time && !wide && row_ok) ? a.rel32[tok0 + i] : 0;
     const long long ti = (wide && row_ok) ? a.ts[tok0 + i] : 0;
     uint32_t bk[8];
-    const AtcChunkClass cl = atc_classify(q0 + sub * 32, j0, L, s_pad, lane);
-    if (cl.all_masked) atc_buckets_all_masked(bk);
-    else if (wide) {
-        if (cl.needs_mask) atc_buckets<true, true>(bk, i, j0, ri, ti, s_rel, s_ts, s_pad, s_thr32, s_thr64, ntime, L, row_ok);
-        else atc_buckets<true, false>(bk, i, j0, ri, ti, s_rel, s_ts, s_pad, s_thr32, s_thr64, ntime, L, row_ok);
-    } else {
-        if (cl.needs_mask) atc_buckets<false, true>(bk, i, j0, ri, ti, s_rel, s_ts, s_pad, s_thr32, s_thr64, ntime, L, row_ok);
-        else atc_buckets<false, false>(bk, i, j0, ri, ti, s_rel, s_ts, s_pad, s_thr32, s_thr64, ntime, L, row_ok);
-    }
+    atc_chunk_buckets(bk, q0 + sub * 32, lane, i, j0, ri, ti, wide, s_rel, a.ts != nullptr ? a.ts + tok0 + j0 : nullptr, s_pad, s_thr32, a.thr64,
+                      ntime, L, row_ok);
     if (row_ok)
         for (int k = 0; k < 32; ++k)
             if (j0 + k < L) out[(size_t)(tok0 + i) * L + j0 + k] = (uint8_t)((bk[k >> 2] >> (8 * (k & 3))) & 0xffu);

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     constexpr int NS = KB <= 2 ? 3 * KB : 5;
     constexpr int D = 64 * KB;
     extern __shared__ unsigned char ce_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ce_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = ce_smem_raw + ((1024u - (smem_u32(ce_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     unsigned char* sX = base;                                   // KB x 16 KB, resident per row block
     unsigned char* sE = sX + KB * TC_TILE_BYTES;                // ring of table slices [128 classes][64 d]
     unsigned char* sOut0 = sE + NS * TC_TILE_BYTES;             // 2 x 32 KB staging (G tiles)

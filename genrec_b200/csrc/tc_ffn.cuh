@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1)
                       const __grid_constant__ CUtensorMap tmH, FfnShape sh, FfnEpiArgs ea) {
     constexpr int D = 64 * KB, NC = 4 * D / 128, NS = FFN_RING;
     extern __shared__ unsigned char ffn_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ffn_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = ffn_smem_raw + ((1024u - (smem_u32(ffn_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     unsigned char* sX = base;                                   // KB x 16 KB: xn tile, K-major, resident per row block
     unsigned char* sW = sX + KB * TC_TILE_BYTES;                // ring of weight slices
     unsigned char* sH0 = sW + NS * TC_TILE_BYTES;               // 2 x 32 KB staging: h chunk = TMA-store source + A operand of MMA 2

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                    const __grid_constant__ CUtensorMap tmC1, TcGemmShape sh, Epi epi) {
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte aligned operand ring, then barriers
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     unsigned char* sA = base;
     unsigned char* sB = base + TC_STAGES * TC_TILE_BYTES;
     unsigned char* sOut0 = base + 2 * TC_STAGES * TC_TILE_BYTES;  // 2 x 64 KB staging (double-buffered), 1024-aligned

@@ -49,7 +49,7 @@ GRB_DEVINL TnItem tn_decode(const TnGroupParams& P, int w) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_tn_group_kernel(const __grid_constant__ TnGroupParams P) {
     extern __shared__ unsigned char tn_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = tn_smem_raw + ((1024u - (smem_u32(tn_smem_raw) & 1023u)) & 1023u)   /* offset from the __shared__ array: keeps the shared address space (LDS / STS) */;
     constexpr int STAGES = 6;
     unsigned char* sA = base;
     unsigned char* sB = base + STAGES * TC_TILE_BYTES;
