@@ -320,13 +320,25 @@ int launch_hstu_attn_bwd(const HstuAttnArgs& a, cudaStream_t st) {
 
 // ---- tcgen05 attention path (attn_tc.cuh): the default whenever the position buckets are uniform (the reference's behaviour)
 //      and head_dim is 32 or 64.  GRB_ATTN=mma selects the first-generation mma.sync kernels (they need the bias_index matrix).
-bool attn_tc_enabled() {
-    const char* e = getenv("GRB_ATTN");   // read on every call so that a test can flip it
-    return !(e && strcmp(e, "mma") == 0);
+// GRB_ATTN = tc | mma | auto (default).  auto: the tcgen05 kernels for seq_len > 256, the mma.sync kernels below - measured on
+// B200 (scripts/bench_attn.py): with 128-row tiles and one thread per TMEM lane a 200-token sequence leaves 40 % of the lanes idle and a
+// CTA lives for only a handful of tiles, so the 64-row mma.sync kernels (5 CTAs per SM) are still ahead there; from ~512 tokens on
+// the tcgen05 path wins and needs no [B, L, L] index.  Read on every call so that a test can flip it.
+int attn_mode() {
+    const char* e = getenv("GRB_ATTN");
+    if (e && strcmp(e, "mma") == 0) return 0;
+    if (e && strcmp(e, "tc") == 0) return 1;
+    return 2;
 }
+bool attn_tc_possible(const grb_hstu_dims* d, const grb_hstu_seq* s);
 bool use_attn_tc(const grb_hstu_dims* d, const grb_hstu_seq* s) {
+    const int mode = attn_mode();
+    if (mode == 0 || (mode == 2 && d->L <= 256 && s->bias_index != nullptr)) return false;
+    return attn_tc_possible(d, s);
+}
+bool attn_tc_possible(const grb_hstu_dims* d, const grb_hstu_seq* s) {
     const int dh = d->D / d->H;
-    return attn_tc_enabled() && s->pos_uniform && (dh == 32 || dh == 64) && d->D % 64 == 0 && s->pad != nullptr && s->time_thr != nullptr &&
+    return s->pos_uniform && (dh == 32 || dh == 64) && d->D % 64 == 0 && s->pad != nullptr && s->time_thr != nullptr &&
            (s->timestamps == nullptr || !s->has_time || (s->rel32 != nullptr && s->wide != nullptr));
 }
 HstuTcArgs make_tc_args(const grb_hstu_dims* d, const float* pos_table, const float* time_table, const grb_hstu_seq* s) {
@@ -680,8 +692,8 @@ int grb_hstu_attention_forward(const grb_hstu_dims* d, const float* pos_table, c
                                const void* P_bf16, void* O_bf16, void* stream) {
     GRB_TRY(check_dims(d));
     GRB_REQUIRE(pos_table && s && P_bf16 && O_bf16, "null argument");
-    GRB_REQUIRE(use_attn_tc(d, s), "the stand-alone attention entry points run the tcgen05 path: uniform position buckets, head_dim 32/64, "
-                                   "pad / time_thr (and rel32 / wide with timestamps) required");
+    GRB_REQUIRE(attn_tc_possible(d, s), "the stand-alone attention entry points run the tcgen05 path: uniform position buckets, head_dim 32/64, "
+                                        "pad / time_thr (and rel32 / wide with timestamps) required");
     GRB_REQUIRE(aligned16(P_bf16) && aligned16(O_bf16), "buffers must be 16-byte aligned");
     return launch_attn_tc_fwd(d, pos_table, time_table, s, (const bf16*)P_bf16, (bf16*)O_bf16, static_cast<cudaStream_t>(stream));
 }
@@ -690,7 +702,7 @@ int grb_hstu_attention_backward(const grb_hstu_dims* d, const float* pos_table, 
                                 float* dtime_table, void* scratch, void* stream) {
     GRB_TRY(check_dims(d));
     GRB_REQUIRE(pos_table && s && P_bf16 && dO_bf16 && dzp_bf16 && dpos_table && scratch, "null argument");
-    GRB_REQUIRE(use_attn_tc(d, s), "the stand-alone attention entry points run the tcgen05 path");
+    GRB_REQUIRE(attn_tc_possible(d, s), "the stand-alone attention entry points run the tcgen05 path");
     GRB_REQUIRE(aligned16(P_bf16) && aligned16(dO_bf16) && aligned16(dzp_bf16) && aligned16(scratch) && (zp_bf16 == nullptr || aligned16(zp_bf16)),
                 "buffers must be 16-byte aligned");
     return launch_attn_tc_bwd(d, pos_table, time_table, s, (const bf16*)P_bf16, (const bf16*)zp_bf16, (const bf16*)dO_bf16, (bf16*)dzp_bf16,

@@ -78,8 +78,8 @@ GRB_DEVINL void nbar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) 
 GRB_DEVINL void nbar_sync_dyn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 GRB_DEVINL void nbar_arrive_dyn(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 // mbarrier wait with a suspend-time hint: a waiting warp sleeps in hardware instead of re-polling (the polls of 8 element-wise
-// warps and of the TMA lane would otherwise take issue slots from the CTA that shares the SM).  Not for the MMA lane: it is the
-// one consumer whose wake-up latency is on the critical path.
+// warps, of the TMA lane and of the MMA lane would otherwise take issue slots from the working warps and from the CTA that shares the
+// SM).  The hint only bounds the sleep: an arrive that completes the phase wakes the waiter.
 GRB_DEVINL void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -346,11 +346,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             constexpr uint32_t idesc_s = umma_idesc(128, 64, 0, 0);    // S half = Q_h K_h[half]^T
             constexpr uint32_t idesc_pv = umma_idesc(128, DH, 0, 1);   // O_h += P V_h   (V: MN-major, DH columns of the box)
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-            mbar_wait(q_full, 0);
+            mbar_wait_sleep(q_full, 0);
             int u = 0, n = 0;                 // units issued, heads whose P V has been issued
             int pend_hb = -1, pend_kt = 0;    // head whose P V is still to be issued
             auto issue_pv = [&](int hb, int kt) {
-                mbar_wait(p_full, n & 1);
+                mbar_wait_sleep(p_full, n & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV);
 #pragma unroll
@@ -365,11 +365,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             for (int kt = 0; kt < nkt; ++kt) {
                 // the single K/V stage is refilled only after the last P V of the previous key tile: flush it before waiting
                 if (pend_hb >= 0) { issue_pv(pend_hb, pend_kt); pend_hb = -1; }
-                mbar_wait(kv_full, kt & 1);
+                mbar_wait_sleep(kv_full, kt & 1);
                 tc_fence_after();
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait(s_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_sleep(s_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)
@@ -594,15 +594,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             constexpr uint32_t idesc_t = umma_idesc(128, DH, 1, 1);     // dV += P^T dO , dK += dS^T Q   (A, B MN-major)
             constexpr uint32_t idesc_q = umma_idesc(128, DH, 0, 1);     // dQ = dS K                     (A K-major, B MN-major)
             const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-            mbar_wait(kv_full, 0);
+            mbar_wait_sleep(kv_full, 0);
             int u = 0, n = 0;
             int pend_hb = -1, pend_it = 0;
             auto second_stage = [&](int hb, int it) {
                 const int st = it & 1;
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 const int buf = n & 1;
-                mbar_wait(pds_full, n & 1);
-                mbar_wait(&dq_free[buf], ((n >> 1) & 1) ^ 1);
+                mbar_wait_sleep(pds_full, n & 1);
+                mbar_wait_sleep(&dq_free[buf], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
@@ -624,12 +624,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             };
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait(&qdo_full[st], (it >> 1) & 1);
+                mbar_wait_sleep(&qdo_full[st], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait(sda_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_sleep(sda_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)

@@ -51,9 +51,11 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 _ZERO_TABLES = {}
 
 
-def attn_legacy() -> bool:
-    """GRB_ATTN=mma selects the first-generation mma.sync attention kernels (kept as an on-device cross-check)."""
-    return os.environ.get("GRB_ATTN", "") == "mma"
+def attn_legacy(L: Optional[int] = None) -> bool:
+    """Which attention kernels will run (GRB_ATTN = tc | mma | auto, see csrc/api.cu attn_mode): True when the mma.sync kernels need
+    their [B, L, ld] bias-index matrix - always for GRB_ATTN=mma, and for seq_len <= 256 in the default auto mode."""
+    mode = os.environ.get("GRB_ATTN", "auto")
+    return mode == "mma" or (mode != "tc" and L is not None and L <= 256)
 
 
 class SeqMeta:
@@ -92,7 +94,7 @@ class SeqMeta:
                 self.wide = torch.empty(B, dtype=torch.uint8, device=dev)
                 check(_lib.load().grb_hstu_seq_prepare(ptr(self.timestamps), ptr(self.pad), B, L, ptr(self.rel32), ptr(self.wide),
                                                        stream_ptr(dev)))
-            if not self.pos_uniform or attn_legacy():
+            if not self.pos_uniform or attn_legacy(L):
                 self._build_bias_index()
 
     def _build_bias_index(self):
@@ -110,7 +112,7 @@ class SeqMeta:
                                               npos_arg, nt, ptr(self.bias_index), self.ld, stream_ptr(dev)))
 
     def struct(self) -> HstuSeq:
-        if self.bias_index is None and attn_legacy():
+        if self.bias_index is None and attn_legacy(self.L):
             self._build_bias_index()
         return HstuSeq(ptr(self.bias_index), self.ld, 1 if self.timestamps is not None else 0, 1 if self.pos_uniform else 0,
                        self.pos_bucket0, ptr(self.timestamps), ptr(self.pad), ptr(self.rel32), ptr(self.wide), ptr(self.time_thr))

@@ -175,7 +175,7 @@ def test_layer_tc_attention_matches_mma_attention(B, L, D, H, monkeypatch):
     dy = torch.randn(B, L, D, device=dev)
     res = []
     for mode in ("tc", "mma"):
-        monkeypatch.setenv("GRB_ATTN", mode)
+        monkeypatch.setenv("GRB_ATTN", mode)      # (the default "auto" picks by sequence length)
         layer.zero_grad(set_to_none=True)
         xi = x.clone().requires_grad_(True)
         y = layer(xi, None, ids == 0, ts)
