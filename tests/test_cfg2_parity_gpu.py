@@ -4,7 +4,7 @@ interleaved forwards, optimizer state)."""
 import pytest
 import torch
 
-from tests.util import make_batch, relerr
+from tests.util import frob_relerr, make_batch, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -86,23 +86,30 @@ def test_cfg2_full_model_vs_oracle():
     loss.backward()
     hook.remove()
     torch.cuda.synchronize()
-    rows = [("loss", abs(loss.item() - lo) / abs(lo), abs(la - lo) / abs(lo)),
-            ("dX into the last block", relerr(got["dx_last"], dxref), relerr(dxac, dxref))]
+    el = abs(loss.item() - lo) / abs(lo)
+    ea = abs(la - lo) / abs(lo)
+    # (name, ours Frobenius, reference-autocast Frobenius, ours max-norm, reference-autocast max-norm)
+    rows = [("loss", el, ea, el, ea),
+            ("dX into the last block", frob_relerr(got["dx_last"], dxref), frob_relerr(dxac, dxref), relerr(got["dx_last"], dxref),
+             relerr(dxac, dxref))]
     for n, q in m.named_parameters():
         ref = gref[n]
         g = q.grad if q.grad is not None else torch.zeros_like(q)
         if ref.abs().max() == 0:
             assert g.abs().max() == 0, n
             continue
-        rows.append((n + ".grad", relerr(g, ref), relerr(gac[n], ref)))
-    lines = ["| tensor | ours vs fp32 oracle | reference-algorithm bf16 autocast vs fp32 | ratio |", "|---|---|---|---|"]
-    lines += [f"| {n} | {a:.2e} | {b:.2e} | {a / max(b, 1e-12):.2f} |" for n, a, b in rows]
+        rows.append((n + ".grad", frob_relerr(g, ref), frob_relerr(gac[n], ref), relerr(g, ref), relerr(gac[n], ref)))
+    lines = ["| tensor | ours, Frobenius | reference autocast, Frobenius | ratio | ours, max-norm | reference autocast, max-norm | ratio |",
+             "|---|---|---|---|---|---|---|"]
+    lines += [f"| {n} | {a:.2e} | {b:.2e} | {a / max(b, 1e-12):.2f} | {c:.2e} | {d:.2e} | {c / max(d, 1e-12):.2f} |" for n, a, b, c, d in rows]
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "error_table_cfg2.md"), "w") as f:
             f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
-    bad = [(n, a, b) for n, a, b in rows if a > 1.0 * b + 1e-3]
+    # relative error in the Frobenius norm (every element counts): ours <= the reference algorithm's own bf16-autocast error;
+    # the max-norm (one worst element out of up to 1.5 M, so noisy between two bf16 paths of equal quality) within 2x of it
+    bad = [(n, a, b, c, d) for n, a, b, c, d in rows if a > 1.0 * b + 5e-4 or c > 2.0 * d + 1e-3]
     assert not bad, bad
     assert torch.isfinite(m.item_embedding.weight.grad).all()
 
