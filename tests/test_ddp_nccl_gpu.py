@@ -30,20 +30,21 @@ def _train(dev, rank, world, group=None):
     torch.manual_seed(0)
     m = HSTU(V, L, D, H, NB, dropout=0.0).to(dev).train()
     opt = FlatAdam(m, lr=1e-3, betas=(0.9, 0.98), process_group=group)
-    import genrec_b200.functional as Fn
-    from genrec_b200.optim import allreduce_gradients
+    import torch.distributed as dist
     per = BG // world
     losses, grads = [], []
     for ids, ts, tg in _batches():
         sl = slice(rank * per, (rank + 1) * per)
         _, loss = m(ids[sl].to(dev), ts[sl].to(dev), tg[sl].to(dev))
         loss.backward()
-        scale = allreduce_gradients(opt.buffers, group)        # what FlatAdam.step() does, split so the gradient can be looked at
-        grads.append((opt.grad * scale).cpu())
-        Fn.adam_step(opt.flat, opt.grad, opt.m, opt.v, opt.mirror, opt.state, opt.lr, 0.9, 0.98, opt.eps, 0.0, scale, True)
+        g = opt.grad.detach().clone()                      # this rank's gradient; averaged over ranks below for the comparison
+        if world > 1:
+            dist.all_reduce(g)
+        grads.append((g / world).cpu())
+        opt.step()                                         # peer-memory one-pass step, or NCCL all-reduce + Adam (GRB_DP=nccl)
         losses.append(loss.detach())
     torch.cuda.synchronize(dev)
-    return opt.flat.detach().cpu().clone(), torch.stack(losses).cpu(), grads
+    return opt.flat.detach().cpu().clone(), torch.stack(losses).cpu(), grads, opt.dp_mode
 
 
 def _worker(rank, world, port, out):
@@ -53,12 +54,13 @@ def _worker(rank, world, port, out):
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    flat, losses, grads = _train(dev, rank, world)
+    flat, losses, grads, mode = _train(dev, rank, world)
     gathered = [torch.zeros_like(losses).to(dev) for _ in range(world)]
     dist.all_gather(gathered, losses.to(dev))
     if rank == 0:
         out["flat"] = flat
         out["grads"] = grads
+        out["mode"] = mode
         out["loss"] = torch.stack([g.cpu() for g in gathered]).mean(0)
     ref = flat.to(dev).clone()
     dist.broadcast(ref, 0)
@@ -66,10 +68,12 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("dp", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_n_rank_nccl_step_equals_single_rank_step(world):
+def test_n_rank_nccl_step_equals_single_rank_step(world, dp, monkeypatch):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("GRB_DP", dp)          # inherited by the spawned ranks
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
@@ -80,8 +84,10 @@ def test_n_rank_nccl_step_equals_single_rank_step(world):
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    flat1, loss1, grads1 = _train(torch.device("cuda:0"), 0, 1)
+    flat1, loss1, grads1, _ = _train(torch.device("cuda:0"), 0, 1)
     assert all(out[f"same{r}"] for r in range(world))
+    print("data-parallel step:", out["mode"])
+    assert out["mode"] == "nccl-allreduce" if dp == "nccl" else out["mode"].startswith(("peer-", "nccl-"))
     torch.testing.assert_close(out["loss"], loss1, rtol=1e-4, atol=1e-5)
     g0, g1 = out["grads"][0], grads1[0]                       # first step: identical parameters, only the reduction order differs
     torch.testing.assert_close(g0, g1, rtol=1e-3, atol=1e-5 * g1.abs().max().item())
