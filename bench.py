@@ -395,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
                 config=dict(workload=workload_name(L) + f" dropout={CFG['dropout']} full train step (emb, blocks, tied logits+CE, bwd, "
                                      f"{'all-reduce, ' if world > 1 else ''}Adam)", name=args.config,
                             global_batch=gb, batch_per_gpu=B, seq_len=L, parallelism=f"dp{world}",
-                            cuda_graph=used_graph,
+                            cuda_graph=used_graph, dp_mode=opt.dp_mode,
                             l2="per-step working set (activations + logits, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                             final_loss=final_loss, ms_per_step_pct=pct_dev),
                 e2e=dict(value=gb * K / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
