@@ -93,6 +93,26 @@ GRB_DEVINL void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(20000u)
         : "memory");
 }
+// The TMA lane and the MMA lane are single threads that mostly wait; a polling loop with an explicit nanosleep keeps them from
+// taking issue slots of the element-wise warps that share their scheduler (the MMA lane sleeps briefly: its wake-up is on the
+// critical path of the next S / dA tile).
+template <int NS>
+GRB_DEVINL void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(NS);
+    }
+}
 GRB_DEVINL uint64_t atc_kmaj(uint32_t addr) { return umma_desc(addr, 16, 1024); }          // K-major box (rows of 128 B)
 GRB_DEVINL uint64_t atc_mnmaj(uint32_t addr) { return umma_desc(addr, ATC_BOX_BYTES, 1024); }  // MN-major, next 64-wide block one box away
 
@@ -193,6 +213,24 @@ GRB_DEVINL bool atc_chunk_buckets(uint32_t (&bk)[8], int q_first, int lane, int 
 GRB_DEVINL void atc_buckets_all_masked(uint32_t (&bk)[8]) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) bk[w] = 0x40404040u;
+}
+
+// Bit k of the result is set when cell k is the LAST of a run of equal bucket bytes (bit 31 always): along a row the log bucket of
+// |ts_i - ts_j| changes every few dozen keys, so the per-cell work that depends on the bucket (the bias fetch, the histogram bin)
+// is done once per run and the common path of a cell is pure fp32 arithmetic.  ~7 integer ops per 4 cells, once per
+// (query tile, key tile) and shared by the heads of the box.
+GRB_DEVINL uint32_t atc_run_ends(const uint32_t (&bk)[8]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t cur = bk[w];
+        const uint32_t nxt = (cur >> 8) | ((w < 7 ? bk[w + 1] : ~cur) << 24);     // byte q of nxt = bucket of cell 4w + q + 1
+        const uint32_t x = cur ^ nxt;                                             // byte q != 0 <=> the run ends at cell 4w + q
+        uint32_t t = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;       // bit 7 of every non-zero byte
+        t = ((t >> 7) * 0x00204081u) >> 21;                                       // gather bits 0, 8, 16, 24 -> bits 0..3
+        m |= (t & 0xfu) << (4 * w);
+    }
+    return m | 0x80000000u;
 }
 
 // per-head bias table: tbl[v] = Wpos[h] + Wtime[v, h] (v < ntime) ; tbl[64] = mask
@@ -334,7 +372,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             mbar_expect_tx(q_full, ATC_BOX_BYTES);
             tma_load_2d(sQ, &tmP, 2 * a.D + box * 64, row_q, q_full);
             for (int kt = 0; kt < nkt; ++kt) {
-                mbar_wait_sleep(kv_empty, (kt & 1) ^ 1);
+                mbar_wait_poll<200>(kv_empty, (kt & 1) ^ 1);
                 mbar_expect_tx(kv_full, 2 * ATC_BOX_BYTES);
                 tma_load_2d(sK, &tmP, 3 * a.D + box * 64, (int)tok0 + kt * 128, kv_full);
                 tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + kt * 128, kv_full);
@@ -346,11 +384,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             constexpr uint32_t idesc_s = umma_idesc(128, 64, 0, 0);    // S half = Q_h K_h[half]^T
             constexpr uint32_t idesc_pv = umma_idesc(128, DH, 0, 1);   // O_h += P V_h   (V: MN-major, DH columns of the box)
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-            mbar_wait_sleep(q_full, 0);
+            mbar_wait_poll<32>(q_full, 0);
             int u = 0, n = 0;                 // units issued, heads whose P V has been issued
             int pend_hb = -1, pend_kt = 0;    // head whose P V is still to be issued
             auto issue_pv = [&](int hb, int kt) {
-                mbar_wait_sleep(p_full, n & 1);
+                mbar_wait_poll<32>(p_full, n & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV);
 #pragma unroll
@@ -365,11 +403,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             for (int kt = 0; kt < nkt; ++kt) {
                 // the single K/V stage is refilled only after the last P V of the previous key tile: flush it before waiting
                 if (pend_hb >= 0) { issue_pv(pend_hb, pend_kt); pend_hb = -1; }
-                mbar_wait_sleep(kv_full, kt & 1);
+                mbar_wait_poll<32>(kv_full, kt & 1);
                 tc_fence_after();
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait_sleep(s_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_poll<32>(s_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)
@@ -426,13 +464,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             const int kb = (kt & 1) * 128;
             const int k0 = kt * 128;
             // bucket bytes of this thread's two chunks (half 0: keys c*32.., half 1: keys 64 + c*32..)
-            uint32_t bk[2][8];
+            uint32_t bk[2][8], ends[2];
             bool masked_all[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
                 masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + kb + cc0,
                                                      g_ts + k0 + cc0, s_pad + kb + cc0, s_thr32, a.thr64, ntime, L, row_ok);
+                ends[half] = atc_run_ends(bk[half]);
             }
             for (int hb = 0; hb < HB; ++hb) {
                 const float* tbl = s_tbl + hb * ATC_TBL_LD;
@@ -451,10 +490,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
                     ++u;
                     if (half == 0 && n > 0) mbar_wait_sleep(p_empty, (n - 1) & 1);   // P V of the previous head has read the P tile
                     if (!masked_all[half]) {
+                        float bias = tbl[bk[half][0] & 0xffu];
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
-                            const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                            s[k] = siluf(s[k] + tbl[bb]);
+                            s[k] = siluf(s[k] + bias);
+                            if (k < 31 && ((ends[half] >> k) & 1u)) bias = tbl[(bk[half][(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu];   // next run
                         }
                         atc_store_chunk(sP, r, half, c, s);
                     } else {
@@ -581,7 +621,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + k0, kv_full);
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait_sleep(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_wait_poll<200>(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[st], 2 * ATC_BOX_BYTES);
                 tma_load_2d(sQ + st * ATC_BOX_BYTES, &tmP, 2 * a.D + box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
                 tma_load_2d(sDO + st * ATC_BOX_BYTES, &tmDO, box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
@@ -594,15 +634,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             constexpr uint32_t idesc_t = umma_idesc(128, DH, 1, 1);     // dV += P^T dO , dK += dS^T Q   (A, B MN-major)
             constexpr uint32_t idesc_q = umma_idesc(128, DH, 0, 1);     // dQ = dS K                     (A K-major, B MN-major)
             const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-            mbar_wait_sleep(kv_full, 0);
+            mbar_wait_poll<32>(kv_full, 0);
             int u = 0, n = 0;
             int pend_hb = -1, pend_it = 0;
             auto second_stage = [&](int hb, int it) {
                 const int st = it & 1;
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 const int buf = n & 1;
-                mbar_wait_sleep(pds_full, n & 1);
-                mbar_wait_sleep(&dq_free[buf], ((n >> 1) & 1) ^ 1);
+                mbar_wait_poll<32>(pds_full, n & 1);
+                mbar_wait_poll<32>(&dq_free[buf], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
@@ -624,12 +664,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             };
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait_sleep(&qdo_full[st], (it >> 1) & 1);
+                mbar_wait_poll<32>(&qdo_full[st], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait_sleep(sda_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_poll<32>(sda_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)
@@ -711,13 +751,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             const bool row_ok = i < L;
             const int ri = ri_next; const long long ti = ti_next;
             if (qt + 1 < nqt) fetch_row(qt + 1);
-            uint32_t bk[2][8];
+            uint32_t bk[2][8], ends[2];
             bool masked_all[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
                 masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + cc0, s_ts + cc0, s_pad + cc0,
                                                      s_thr32, a.thr64, ntime, L, row_ok);
+                ends[half] = atc_run_ends(bk[half]);
             }
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb) {
@@ -739,49 +780,35 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                     ++u;
                     if (half == 0 && n > 0) mbar_wait_sleep(pds_empty, (n - 1) & 1);
                     if (!masked_all[half]) {
+                        // Per run of equal buckets: one bias fetch at its start, one histogram update at its end.  Bias-table
+                        // gradients: every element-wise thread owns a private column of 32 bins per head in shared memory (plain
+                        // read-modify-write, bank-conflict free); the wide (64-bit) path sends its runs to global memory.
+                        float bias = tbl[bk[half][0] & 0xffu];
+                        float acc = 0.f;
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
-                            const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                            const float x = s[k] + tbl[bb];
+                            const float x = s[k] + bias;
                             const float sg = sigmoidf_fast(x);
                             s[k] = x * sg;                                      // A
                             da[k] = da[k] * (sg * (1.f + x * (1.f - sg)));      // dS (exactly 0 on masked cells)
+                            acc += da[k];
+                            if ((ends[half] >> k) & 1u) {
+                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;   // bucket of the run that ends here
+                                if (!wide) {
+                                    hist[(bb & 31u) * 256] += acc;             // masked runs (64) add an exact 0 to bin 0
+                                } else if (acc != 0.f) {
+                                    pos_acc[hb] += acc;
+                                    if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, acc);
+                                }
+                                acc = 0.f;
+                                if (k < 31) bias = tbl[(bk[half][(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu];
+                            }
                         }
                         atc_store_chunk(sP, r, half, c, s);
                         atc_store_chunk(sDS, r, half, c, da);
                     } else {
                         atc_store_chunk_zero(sP, r, half, c);
                         atc_store_chunk_zero(sDS, r, half, c);
-                    }
-                    // bias-table gradients.  Every element-wise thread owns a private column of 32 bins per head in shared memory
-                    // (plain read-modify-write, bank-conflict free, no atomics).  Consecutive keys of a row mostly fall into the
-                    // same log bucket, so runs are summed in a register and only run ends touch shared memory - a handful of
-                    // updates per 32 cells instead of a chain of 32 dependent read-modify-writes.
-                    if (!masked_all[half]) {
-                        if (!wide) {
-                            unsigned prev = bk[half][0] & 31u;
-                            float acc = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                const unsigned bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 31u;   // masked cells (64) add an exact 0 to bin 0
-                                if (bb != prev) {
-                                    hist[prev * 256] += acc;
-                                    prev = bb;
-                                    acc = 0.f;
-                                }
-                                acc += da[k];
-                            }
-                            hist[prev * 256] += acc;
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
-                                if (da[k] != 0.f) {
-                                    pos_acc[hb] += da[k];
-                                    if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, da[k]);
-                                }
-                            }
-                        }
                     }
                 }
                 fence_proxy_async();
