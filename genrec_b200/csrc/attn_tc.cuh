@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             mbar_expect_tx(q_full, ATC_BOX_BYTES);
             tma_load_2d(sQ, &tmP, 2 * a.D + box * 64, row_q, q_full);
             for (int kt = 0; kt < nkt; ++kt) {
-                mbar_wait_poll<200>(kv_empty, (kt & 1) ^ 1);
+                mbar_wait_sleep(kv_empty, (kt & 1) ^ 1);
                 mbar_expect_tx(kv_full, 2 * ATC_BOX_BYTES);
                 tma_load_2d(sK, &tmP, 3 * a.D + box * 64, (int)tok0 + kt * 128, kv_full);
                 tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + kt * 128, kv_full);
@@ -384,11 +384,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             constexpr uint32_t idesc_s = umma_idesc(128, 64, 0, 0);    // S half = Q_h K_h[half]^T
             constexpr uint32_t idesc_pv = umma_idesc(128, DH, 0, 1);   // O_h += P V_h   (V: MN-major, DH columns of the box)
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-            mbar_wait_poll<32>(q_full, 0);
+            mbar_wait_sleep(q_full, 0);
             int u = 0, n = 0;                 // units issued, heads whose P V has been issued
             int pend_hb = -1, pend_kt = 0;    // head whose P V is still to be issued
             auto issue_pv = [&](int hb, int kt) {
-                mbar_wait_poll<32>(p_full, n & 1);
+                mbar_wait_sleep(p_full, n & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV);
 #pragma unroll
@@ -403,11 +403,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             for (int kt = 0; kt < nkt; ++kt) {
                 // the single K/V stage is refilled only after the last P V of the previous key tile: flush it before waiting
                 if (pend_hb >= 0) { issue_pv(pend_hb, pend_kt); pend_hb = -1; }
-                mbar_wait_poll<32>(kv_full, kt & 1);
+                mbar_wait_sleep(kv_full, kt & 1);
                 tc_fence_after();
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait_poll<32>(s_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_sleep(s_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             tma_load_2d(sV, &tmP, a.D + box * 64, (int)tok0 + k0, kv_full);
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait_poll<200>(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_wait_sleep(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[st], 2 * ATC_BOX_BYTES);
                 tma_load_2d(sQ + st * ATC_BOX_BYTES, &tmP, 2 * a.D + box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
                 tma_load_2d(sDO + st * ATC_BOX_BYTES, &tmDO, box * 64, (int)tok0 + qt * 128, &qdo_full[st]);
@@ -634,15 +634,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             constexpr uint32_t idesc_t = umma_idesc(128, DH, 1, 1);     // dV += P^T dO , dK += dS^T Q   (A, B MN-major)
             constexpr uint32_t idesc_q = umma_idesc(128, DH, 0, 1);     // dQ = dS K                     (A K-major, B MN-major)
             const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-            mbar_wait_poll<32>(kv_full, 0);
+            mbar_wait_sleep(kv_full, 0);
             int u = 0, n = 0;
             int pend_hb = -1, pend_it = 0;
             auto second_stage = [&](int hb, int it) {
                 const int st = it & 1;
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 const int buf = n & 1;
-                mbar_wait_poll<32>(pds_full, n & 1);
-                mbar_wait_poll<32>(&dq_free[buf], ((n >> 1) & 1) ^ 1);
+                mbar_wait_sleep(pds_full, n & 1);
+                mbar_wait_sleep(&dq_free[buf], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
@@ -664,12 +664,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             };
             for (int qt = kt, it = 0; qt < nqt; ++qt, ++it) {
                 const int st = it & 1;
-                mbar_wait_poll<32>(&qdo_full[st], (it >> 1) & 1);
+                mbar_wait_sleep(&qdo_full[st], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(sQ + st * ATC_BOX_BYTES), do_addr = smem_u32(sDO + st * ATC_BOX_BYTES);
                 for (int hb = 0; hb < HB; ++hb) {
                     for (int half = 0; half < 2; ++half) {
-                        if (u > 0) mbar_wait_poll<32>(sda_free, (u - 1) & 1);
+                        if (u > 0) mbar_wait_sleep(sda_free, (u - 1) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int s = 0; s < KS; ++s)
