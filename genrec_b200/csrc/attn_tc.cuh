@@ -93,26 +93,6 @@ GRB_DEVINL void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(20000u)
         : "memory");
 }
-// The TMA lane and the MMA lane are single threads that mostly wait; a polling loop with an explicit nanosleep keeps them from
-// taking issue slots of the element-wise warps that share their scheduler (the MMA lane sleeps briefly: its wake-up is on the
-// critical path of the next S / dA tile).
-template <int NS>
-GRB_DEVINL void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(NS);
-    }
-}
 GRB_DEVINL uint64_t atc_kmaj(uint32_t addr) { return umma_desc(addr, 16, 1024); }          // K-major box (rows of 128 B)
 GRB_DEVINL uint64_t atc_mnmaj(uint32_t addr) { return umma_desc(addr, ATC_BOX_BYTES, 1024); }  // MN-major, next 64-wide block one box away
 
@@ -213,24 +193,6 @@ GRB_DEVINL bool atc_chunk_buckets(uint32_t (&bk)[8], int q_first, int lane, int 
 GRB_DEVINL void atc_buckets_all_masked(uint32_t (&bk)[8]) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) bk[w] = 0x40404040u;
-}
-
-// Bit k of the result is set when cell k is the LAST of a run of equal bucket bytes (bit 31 always): along a row the log bucket of
-// |ts_i - ts_j| changes every few dozen keys, so the per-cell work that depends on the bucket (the bias fetch, the histogram bin)
-// is done once per run and the common path of a cell is pure fp32 arithmetic.  ~7 integer ops per 4 cells, once per
-// (query tile, key tile) and shared by the heads of the box.
-GRB_DEVINL uint32_t atc_run_ends(const uint32_t (&bk)[8]) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const uint32_t cur = bk[w];
-        const uint32_t nxt = (cur >> 8) | ((w < 7 ? bk[w + 1] : ~cur) << 24);     // byte q of nxt = bucket of cell 4w + q + 1
-        const uint32_t x = cur ^ nxt;                                             // byte q != 0 <=> the run ends at cell 4w + q
-        uint32_t t = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;       // bit 7 of every non-zero byte
-        t = ((t >> 7) * 0x00204081u) >> 21;                                       // gather bits 0, 8, 16, 24 -> bits 0..3
-        m |= (t & 0xfu) << (4 * w);
-    }
-    return m | 0x80000000u;
 }
 
 // per-head bias table: tbl[v] = Wpos[h] + Wtime[v, h] (v < ntime) ; tbl[64] = mask
@@ -464,14 +426,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
             const int kb = (kt & 1) * 128;
             const int k0 = kt * 128;
             // bucket bytes of this thread's two chunks (half 0: keys c*32.., half 1: keys 64 + c*32..)
-            uint32_t bk[2][8], ends[2];
+            uint32_t bk[2][8];
             bool masked_all[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
                 masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + kb + cc0,
                                                      g_ts + k0 + cc0, s_pad + kb + cc0, s_thr32, a.thr64, ntime, L, row_ok);
-                ends[half] = atc_run_ends(bk[half]);
             }
             for (int hb = 0; hb < HB; ++hb) {
                 const float* tbl = s_tbl + hb * ATC_TBL_LD;
@@ -490,11 +451,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) hstu_attn_tc_fwd_kernel(const 
                     ++u;
                     if (half == 0 && n > 0) mbar_wait_sleep(p_empty, (n - 1) & 1);   // P V of the previous head has read the P tile
                     if (!masked_all[half]) {
-                        float bias = tbl[bk[half][0] & 0xffu];
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
-                            s[k] = siluf(s[k] + bias);
-                            if (k < 31 && ((ends[half] >> k) & 1u)) bias = tbl[(bk[half][(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu];   // next run
+                            const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                            s[k] = siluf(s[k] + tbl[bb]);
                         }
                         atc_store_chunk(sP, r, half, c, s);
                     } else {
@@ -751,14 +711,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             const bool row_ok = i < L;
             const int ri = ri_next; const long long ti = ti_next;
             if (qt + 1 < nqt) fetch_row(qt + 1);
-            uint32_t bk[2][8], ends[2];
+            uint32_t bk[2][8];
             bool masked_all[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int cc0 = half * 64 + c * 32;
                 masked_all[half] = atc_chunk_buckets(bk[half], q0 + sub * 32, lane, i, k0 + cc0, ri, ti, wide, s_rel + cc0, s_ts + cc0, s_pad + cc0,
                                                      s_thr32, a.thr64, ntime, L, row_ok);
-                ends[half] = atc_run_ends(bk[half]);
             }
 #pragma unroll
             for (int hb = 0; hb < HB; ++hb) {
@@ -780,35 +739,49 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                     ++u;
                     if (half == 0 && n > 0) mbar_wait_sleep(pds_empty, (n - 1) & 1);
                     if (!masked_all[half]) {
-                        // Per run of equal buckets: one bias fetch at its start, one histogram update at its end.  Bias-table
-                        // gradients: every element-wise thread owns a private column of 32 bins per head in shared memory (plain
-                        // read-modify-write, bank-conflict free); the wide (64-bit) path sends its runs to global memory.
-                        float bias = tbl[bk[half][0] & 0xffu];
-                        float acc = 0.f;
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
-                            const float x = s[k] + bias;
+                            const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                            const float x = s[k] + tbl[bb];
                             const float sg = sigmoidf_fast(x);
                             s[k] = x * sg;                                      // A
                             da[k] = da[k] * (sg * (1.f + x * (1.f - sg)));      // dS (exactly 0 on masked cells)
-                            acc += da[k];
-                            if ((ends[half] >> k) & 1u) {
-                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;   // bucket of the run that ends here
-                                if (!wide) {
-                                    hist[(bb & 31u) * 256] += acc;             // masked runs (64) add an exact 0 to bin 0
-                                } else if (acc != 0.f) {
-                                    pos_acc[hb] += acc;
-                                    if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, acc);
-                                }
-                                acc = 0.f;
-                                if (k < 31) bias = tbl[(bk[half][(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu];
-                            }
                         }
                         atc_store_chunk(sP, r, half, c, s);
                         atc_store_chunk(sDS, r, half, c, da);
                     } else {
                         atc_store_chunk_zero(sP, r, half, c);
                         atc_store_chunk_zero(sDS, r, half, c);
+                    }
+                    // bias-table gradients.  Every element-wise thread owns a private column of 32 bins per head in shared memory
+                    // (plain read-modify-write, bank-conflict free, no atomics).  Consecutive keys of a row mostly fall into the
+                    // same log bucket, so runs are summed in a register and only run ends touch shared memory - a handful of
+                    // updates per 32 cells instead of a chain of 32 dependent read-modify-writes.
+                    if (!masked_all[half]) {
+                        if (!wide) {
+                            unsigned prev = bk[half][0] & 31u;
+                            float acc = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const unsigned bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 31u;   // masked cells (64) add an exact 0 to bin 0
+                                if (bb != prev) {
+                                    hist[prev * 256] += acc;
+                                    prev = bb;
+                                    acc = 0.f;
+                                }
+                                acc += da[k];
+                            }
+                            hist[prev * 256] += acc;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const uint32_t bb = (bk[half][k >> 2] >> (8 * (k & 3))) & 0xffu;
+                                if (da[k] != 0.f) {
+                                    pos_acc[hb] += da[k];
+                                    if (a.dwtime != nullptr && ntime > 0 && bb < 64u) atomicAdd(a.dwtime + (size_t)bb * a.H + box * HB + hb, da[k]);
+                                }
+                            }
+                        }
                     }
                 }
                 fence_proxy_async();
