@@ -257,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)  # identical init on every rank (DDP broadcast equivalent)
     model = HSTU(**{**CFG, "max_seq_len": L}).to(dev).train()
     # plain loss.backward() every step: the head may accumulate straight into the flat gradient buffer (checked on the device)
-    opt = FlatAdam(model, lr=1e-3, betas=(0.9, 0.98), unit_loss_grad=True)
+    opt = FlatAdam(model, lr=1e-3, betas=(0.9, 0.98), unit_loss_grad=True, defer_weight_grads=os.environ.get("GRB_DEFER", "1") != "0")
 
     nb = 8
     host = [tuple(t.pin_memory() for t in synth_batch(B, L, V, 1000 * rank + i)) for i in range(nb)]
@@ -436,6 +436,7 @@ def block_roofline(model, B, L, dev, K):
         for layer in model.layers:
             y = layer(y, None, None, ts, _meta=meta, _seed=seed, _seed_dev=seed_dev)
         y.backward(dy)
+        Fn.join_deferred(dev)      # the weight-gradient GEMMs belong to the stack's work: inside the timed region
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())

@@ -50,6 +50,8 @@ SIGNATURES = {
     "grb_version": (c_int, []),
     "grb_launch_count": (c_u64, []),
     "grb_check_device": (c_int, [c_int]),
+    "grb_set_defer_weight_grads": (c_int, [c_int]),
+    "grb_join_deferred": (c_int, [c_void_p]),
     "grb_hstu_layer_saved_bytes": (c_size_t, [P(HstuDims)]),
     "grb_hstu_layer_workspace_bytes": (c_size_t, [P(HstuDims)]),
     "grb_hstu_layer_forward": (c_int, [P(HstuDims), P(HstuLayerParams), P(HstuSeq), c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -275,6 +275,41 @@ SideStream& side_stream() {
     static thread_local SideStream ss;   // the backward runs on the autograd thread: one side stream per calling thread
     return ss;
 }
+// ---- deferred weight gradients.  dW / dE GEMMs are not on the critical path of a training step: nothing reads them before the
+// optimizer.  With grb_set_defer_weight_grads(1) they go to a per-device side stream, forked where their operands are ready and
+// joined by grb_join_deferred() (FlatAdam.step calls it), so they fill the SM tails of the epilogue-bound GEMMs and run next to the
+// issue-bound attention kernels; the 620 MB dlogits stream of the head's dE GEMM overlaps the last block's backward.  The CALLER keeps
+// the operand buffers (layer workspace, saved blob, head workspace) alive until the join.  Works under CUDA-graph capture (event
+// fork / join pulls the side stream into the capture).
+struct DeferStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false, pending = false;
+};
+std::mutex g_defer_mu;
+bool g_defer_on = false;
+DeferStream& defer_stream() {
+    static DeferStream ds[64];
+    return ds[current_device() & 63];
+}
+// run `launch(side_stream)` after everything enqueued on `st` so far; returns 0 / error code
+template <class F>
+int defer_run(cudaStream_t st, F&& launch) {
+    std::lock_guard<std::mutex> lock(g_defer_mu);
+    DeferStream& d = defer_stream();
+    if (!d.ok) {
+        GRB_CUDA(cudaStreamCreateWithFlags(&d.s, cudaStreamNonBlocking));
+        GRB_CUDA(cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming));
+        GRB_CUDA(cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming));
+        d.ok = true;
+    }
+    GRB_CUDA(cudaEventRecord(d.fork, st));
+    GRB_CUDA(cudaStreamWaitEvent(d.s, d.fork, 0));
+    GRB_TRY(launch(d.s));
+    GRB_CUDA(cudaEventRecord(d.join, d.s));
+    d.pending = true;
+    return 0;
+}
 bool use_side_stream() {
     static int v = -1;
     if (v < 0) {
@@ -637,7 +672,14 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
         TnSpec specs[3] = {{w.dyb, sv.hact, g->ffn2_w, D, 4 * D, T, D, 4 * D, 4 * D},
                            {w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, D},
                            {w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, D}};
-        GRB_CUDA(launch_tc_tn_group(specs, 3, sm_count(), st));
+        if (g_defer_on) {
+            GRB_TRY(defer_run(st, [&](cudaStream_t side) -> int {
+                GRB_CUDA(launch_tc_tn_group(specs, 3, sm_count(), side));
+                return 0;
+            }));
+        } else {
+            GRB_CUDA(launch_tc_tn_group(specs, 3, sm_count(), st));
+        }
     }
     (void)nodrop;
     return 0;
@@ -654,6 +696,21 @@ int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int
                                                                                  reinterpret_cast<const long long*>(time_thr), pos_bucket, L,
                                                                                  ld_index, npos, ntime, out);
     GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int grb_set_defer_weight_grads(int on) {
+    std::lock_guard<std::mutex> lock(g_defer_mu);
+    g_defer_on = on != 0;
+    return 0;
+}
+int grb_join_deferred(void* stream) {
+    std::lock_guard<std::mutex> lock(g_defer_mu);
+    DeferStream& d = defer_stream();
+    if (d.ok && d.pending) {
+        GRB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), d.join, 0));
+        d.pending = false;
+    }
     return 0;
 }
 
@@ -796,7 +853,14 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     {
         if (use_tc()) {
             TnSpec spec{h.logits, h.xf, dtable, C, D, T, h.ldl, D, D};  // dE[C,D] += dlogits^T xf
-            GRB_CUDA(launch_tc_tn_group(&spec, 1, sm_count(), st));
+            if (g_defer_on) {
+                GRB_TRY(defer_run(st, [&](cudaStream_t side) -> int {
+                    GRB_CUDA(launch_tc_tn_group(&spec, 1, sm_count(), side));
+                    return 0;
+                }));
+            } else {
+                GRB_CUDA(launch_tc_tn_group(&spec, 1, sm_count(), st));
+            }
         } else {
             GRB_CUDA(gemm_tn_atomic(h.logits, h.xf, dtable, C, D, T, h.ldl, D, st));
         }

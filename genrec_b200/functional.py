@@ -32,6 +32,32 @@ def require_i64(*tensors) -> None:
             raise _lib.GrbError(f"genrec_b200 error -1: ids / targets / timestamps must be int64 (got {t.dtype})")
 
 
+# ---- deferred weight gradients (see grb_set_defer_weight_grads): operand buffers of GEMMs that run on the library's side stream
+#      are parked here until join_deferred(), so the caching allocator cannot hand them to later kernels of the main stream
+_DEFER = {"on": False, "c": False, "keep": []}
+
+
+def set_defer_weight_grads(on: bool) -> None:
+    """Policy switch (FlatAdam(defer_weight_grads=True)); the library-side flag is raised per call, only for calls whose gradients go
+    to the flat gradient sink (nothing but the optimizer reads those before the join)."""
+    _DEFER["on"] = bool(on)
+
+
+def _defer_for_call(active: bool) -> bool:
+    if _DEFER["c"] != active:
+        check(_lib.load().grb_set_defer_weight_grads(1 if active else 0))
+        _DEFER["c"] = active
+    return active
+
+
+def join_deferred(device) -> None:
+    """Make the deferred dW / dE GEMMs visible to the current stream of `device` and release their operand buffers."""
+    if _DEFER["c"] or _DEFER["keep"]:
+        with torch.cuda.device(device):
+            check(_lib.load().grb_join_deferred(stream_ptr(device)))
+        _DEFER["keep"].clear()
+
+
 def _u8(n, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
@@ -189,9 +215,12 @@ class HstuLayerFn(torch.autograd.Function):
         dx = torch.empty_like(dyc)
         ws = _u8(lib.grb_hstu_layer_workspace_bytes(C.byref(dims)), dy.device)
         seq = meta.struct()
+        deferred = _defer_for_call(_DEFER["on"] and sink is not None)
         with torch.cuda.device(dy.device):
             check(lib.grb_hstu_layer_backward(C.byref(dims), C.byref(pstruct), C.byref(seq), ptr(dyc), ptr(ctx.saved_blob), ptr(dx),
                                               C.byref(gstruct), ptr(ws), stream_ptr(dy.device)))
+        if deferred:
+            _DEFER["keep"].append((ws, ctx.saved_blob, dyc))     # still read by the deferred dW GEMM
         ctx.saved_blob = None
         if sink is not None:
             return (dx, None, None, None, *([None] * len(PARAM_ORDER)))
@@ -280,10 +309,13 @@ class HeadLossFn(torch.autograd.Function):
             db = torch.zeros_like(ln_b, dtype=torch.float32)
         else:
             dx = dtable = dg = db = None
+        deferred = _defer_for_call(_DEFER["on"] and direct)
         with torch.cuda.device(x.device):
             check(lib.grb_head_loss_forward_backward(ptr(xc), ptr(ln_g.detach()), ptr(ln_b.detach()), float(eps), ptr(table_bf16), ptr(tg),
                                                      T, D, Cn, ptr(loss), ptr(dx), ptr(dtable), ptr(dg), ptr(db), ptr(ws),
                                                      stream_ptr(x.device)))
+        if deferred:
+            _DEFER["keep"].append((ws, xc))                       # dlogits / xf are still read by the deferred dE GEMM
         ctx.grads = (dx, dg, db, dtable)
         return loss
 

@@ -113,11 +113,14 @@ class PeerMemory:
 class FlatAdam:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, process_group=None, grad_sink: bool = True, unit_loss_grad: bool = False,
-                 peer_memory: Optional[bool] = None):
+                 peer_memory: Optional[bool] = None, defer_weight_grads: bool = False):
         """``unit_loss_grad=True`` promises that every training forward is followed by exactly one ``loss.backward()`` with
         gradient 1 (no loss scaling, no gradient accumulation through a scaled loss): the fused head then accumulates its
         parameter gradients into the flat buffer in the same pass that computes the loss.  The promise is checked on the
-        device (``grb_assert_unit_scalar``).  Default False: fully general, a few microseconds slower per step."""
+        device (``grb_assert_unit_scalar``).  Default False: fully general, a few microseconds slower per step.
+        ``defer_weight_grads=True`` moves the dW / dE GEMMs of the backward pass to a side stream that ``step()`` joins (they are not
+        on the critical path); anything else that reads ``.grad`` / the flat gradient before ``step()`` must call
+        ``sync_grads()`` first.  Process-wide switch (``grb_set_defer_weight_grads``)."""
         dev0 = next(p for p in model.parameters() if p.requires_grad).device
         assert dev0.type == "cuda", "FlatAdam drives CUDA kernels; move the model to the GPU first"
         # data-parallel step: one pass over NVLink peer memory (multimem reduce + Adam + multicast parameter store, csrc/dp_adam.cuh)
@@ -161,6 +164,9 @@ class FlatAdam:
         # the kernels read the bf16 mirror, never the fp32 masters: anything that rewrites the masters behind the optimizer's
         # back (load_state_dict on resume, accelerate.load_state) must refresh it
         self._hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_mirror())
+        if defer_weight_grads:
+            assert grad_sink, "deferred weight gradients need the gradient sink (nothing but this optimizer consumes them)"
+            Fn.set_defer_weight_grads(True)
 
     def mirror_of(self, p: torch.Tensor) -> torch.Tensor:
         return self.buffers.mirror_of(p)
@@ -182,10 +188,15 @@ class FlatAdam:
         torch.cuda.synchronize(b.device)
         dist.barrier(pm.group)
 
+    def sync_grads(self) -> None:
+        """Wait (on the current stream) for gradient work that was deferred to the side stream."""
+        Fn.join_deferred(self.flat.device)
+
     def step(self) -> None:
         """world == 1: fused Adam.  world > 1: reduce + Adam + parameter broadcast in one pass over peer memory (dp_mode "peer-*"),
         or all-reduce(SUM) -> fused Adam with grad_scale = 1/world (dp_mode "nccl-allreduce"); either way the bf16 mirror is
         refreshed and the flat gradient is zero afterwards."""
+        Fn.join_deferred(self.flat.device)
         if self.peer is not None:
             pg, pp, pmir, psig = self._peer_ptrs
             with torch.cuda.device(self.flat.device):

@@ -114,6 +114,14 @@ int grb_hstu_attention_backward(const grb_hstu_dims* d, const float* pos_table, 
 int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int64_t* time_thr, const uint8_t* pos_bucket, int B,
                         int L, int npos, int ntime, uint16_t* out, int ld_index, void* stream);
 
+/* Weight-gradient GEMMs (dW of a block, dE of the head) off the critical path: with grb_set_defer_weight_grads(1) they are enqueued
+ * on a library-owned side stream, forked from the caller's stream where their operands are ready, and become visible to the
+ * caller's stream only after grb_join_deferred(stream).  The caller must keep the operand buffers of the deferred work (the
+ * `workspace` and `saved` blobs of grb_hstu_layer_backward, the workspace of grb_head_loss_forward_backward) alive until then.
+ * CUDA-graph capturable (event fork / join).  Off by default: every entry point is then complete when its stream work is. */
+int grb_set_defer_weight_grads(int on);
+int grb_join_deferred(void* stream);
+
 size_t grb_hstu_layer_saved_bytes(const grb_hstu_dims* d);
 size_t grb_hstu_layer_workspace_bytes(const grb_hstu_dims* d);
 int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* p, const grb_hstu_seq* s,

@@ -242,3 +242,33 @@ def test_flat_adam_state_dict_and_mirror_refresh():
         m2.layers[0].ffn[0].weight.data.mul_(0.0)
     o2.refresh_mirror()
     assert o2.mirror_of(m2.layers[0].ffn[0].weight).abs().max() == 0
+
+
+def test_deferred_weight_gradients_equal_inline_ones():
+    """FlatAdam(defer_weight_grads=True): dW / dE GEMMs run on the library's side stream and are joined by step(); gradients and
+    the parameter update must equal the inline schedule."""
+    from genrec_b200.hstu import HSTU
+    from genrec_b200.optim import FlatAdam
+    import genrec_b200.functional as Fn
+    dev = torch.device("cuda:0")
+    ids, ts, tg = make_batch(6, 70, 300, seed=1, pad=True, device=dev)
+    res = []
+    try:
+        for defer in (False, True):
+            torch.manual_seed(0)
+            m = HSTU(300, 70, 64, 2, 2, dropout=0.0).to(dev).train()
+            opt = FlatAdam(m, lr=1e-3, unit_loss_grad=True, defer_weight_grads=defer)
+            Fn.set_defer_weight_grads(defer)
+            for _ in range(2):
+                _, loss = m(ids, ts, tg)
+                loss.backward()
+                opt.sync_grads()
+                g = opt.grad.clone()
+                opt.step()
+            torch.cuda.synchronize()
+            res.append((g, opt.flat.clone()))
+    finally:
+        Fn.set_defer_weight_grads(False)
+        Fn.join_deferred(dev)
+    torch.testing.assert_close(res[1][0], res[0][0], rtol=1e-3, atol=1e-5 * res[0][0].abs().max().item())
+    assert ((res[1][1] - res[0][1]).abs() > 1e-4).float().mean().item() < 1e-3
