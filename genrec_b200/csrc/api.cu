@@ -631,7 +631,12 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
         GRB_CUDA(gemm_dact(1, w.dyb, (const bf16*)p->ffn2_w, sv.z1, w.dz1, T, 4 * D, D, drop_hid, st));  // dz1 = dropmask(dyb W2) * silu'(z1)
     }
     // FFN first linear
-    GRB_TRY(colsum(w.dz1, T, 4 * D, 4 * D, g->ffn1_b, st));
+    // bias gradients are off the critical path too: with deferred weight gradients the column sums run beside the main chain
+    auto colsum_maybe_deferred = [&](const bf16* in, float* out) -> int {
+        if (use_tc() && g_defer_on) return defer_run(st, [&](cudaStream_t side) -> int { return colsum(in, T, 4 * D, 4 * D, out, side); });
+        return colsum(in, T, 4 * D, 4 * D, out, st);
+    };
+    GRB_TRY(colsum_maybe_deferred(w.dz1, g->ffn1_b));
     {
         if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dz1, sv.xn, g->ffn1_w, 4 * D, D, T, 4 * D, D, st));  // dW1[4D,D] += dz1^T xn
     }
@@ -660,7 +665,7 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
         else GRB_TRY(launch_hstu_attn_bwd<64>(a, st));
     }
     // projection
-    GRB_TRY(colsum(w.dzp, T, 4 * D, 4 * D, g->proj_b, st));
+    GRB_TRY(colsum_maybe_deferred(w.dzp, g->proj_b));
     {
         if (!use_tc()) GRB_CUDA(gemm_tn_atomic(w.dzp, sv.xb, g->proj_w, 4 * D, D, T, 4 * D, D, st));  // dWp[4D,D] += dzp^T xb
     }
