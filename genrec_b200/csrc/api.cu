@@ -310,6 +310,15 @@ int defer_run(cudaStream_t st, F&& launch) {
     d.pending = true;
     return 0;
 }
+int join_pending(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_defer_mu);
+    DeferStream& d = defer_stream();
+    if (d.ok && d.pending) {
+        GRB_CUDA(cudaStreamWaitEvent(st, d.join, 0));
+        d.pending = false;
+    }
+    return 0;
+}
 bool use_side_stream() {
     static int v = -1;
     if (v < 0) {
@@ -571,6 +580,7 @@ int grb_hstu_layer_forward(const grb_hstu_dims* d, const grb_hstu_layer_params* 
         GRB_CUDA(gemm_bias_act(1, sv.xb, (const bf16*)p->proj_w, p->proj_b, sv.zp, sv.P, T, 4 * D, D, nodrop, st));
     }
     // 3. O = silu(Q K^T + bias) V, causal + key padding                                      (hstu.py:244-267)
+    GRB_TRY(join_pending(st));   // a bias-index matrix built on the side stream (deferred schedule) must be complete
     if (attn_tc) {
         GRB_TRY(launch_attn_tc_fwd(d, p->pos_table, p->time_table, s, sv.P, sv.O, st));
     } else {
@@ -697,11 +707,16 @@ int grb_hstu_bias_index(const int64_t* timestamps, const uint8_t* pad, const int
     GRB_REQUIRE(ld_index >= L && ld_index % 8 == 0, "ld_index must be a multiple of 8 and >= L");
     GRB_REQUIRE(ntime >= 0 && ntime <= ATT_MAX_BUCKETS && npos >= 1 && npos <= ATT_MAX_BUCKETS, "bucket counts out of range");
     dim3 grid((ld_index + 255) / 256, (L + 7) / 8, B);
-    launch_k(hstu_bias_index_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(timestamps), pad,
-                                                                                 reinterpret_cast<const long long*>(time_thr), pos_bucket, L,
-                                                                                 ld_index, npos, ntime, out);
-    GRB_CUDA(cudaGetLastError());
-    return 0;
+    auto go = [&](cudaStream_t s_) -> int {
+        launch_k(hstu_bias_index_kernel, grid, 256, 0, s_, reinterpret_cast<const long long*>(timestamps), pad,
+                 reinterpret_cast<const long long*>(time_thr), pos_bucket, L, ld_index, npos, ntime, out);
+        GRB_CUDA(cudaGetLastError());
+        return 0;
+    };
+    // the index matrix is first needed by the attention kernel of the first block: with the deferred schedule it is built beside
+    // that block's cast + projection GEMM (grb_hstu_layer_forward joins before its attention launch)
+    if (g_defer_on) return defer_run(static_cast<cudaStream_t>(stream), go);
+    return go(static_cast<cudaStream_t>(stream));
 }
 
 int grb_set_defer_weight_grads(int on) {
@@ -709,15 +724,7 @@ int grb_set_defer_weight_grads(int on) {
     g_defer_on = on != 0;
     return 0;
 }
-int grb_join_deferred(void* stream) {
-    std::lock_guard<std::mutex> lock(g_defer_mu);
-    DeferStream& d = defer_stream();
-    if (d.ok && d.pending) {
-        GRB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), d.join, 0));
-        d.pending = false;
-    }
-    return 0;
-}
+int grb_join_deferred(void* stream) { return join_pending(static_cast<cudaStream_t>(stream)); }
 
 int grb_hstu_seq_prepare(const int64_t* timestamps, const uint8_t* pad, int B, int L, int32_t* rel32, uint8_t* wide, void* stream) {
     GRB_REQUIRE(timestamps && pad && rel32 && wide, "null argument");
@@ -830,12 +837,21 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     GRB_REQUIRE(!want_grad || (dtable && dln_g && dln_b), "null gradient pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     HeadWork h = carve_head(workspace, T, D, C);
+    // the target count (one CTA, latency-bound) depends on the targets only: with the deferred schedule it runs beside the final
+    // LayerNorm and is joined before the fused CE kernel
+    const bool count_aside = g_defer_on;
+    auto count = [&](cudaStream_t s_) -> int {
+        launch_k(ce_count_kernel, 1, 1024, 0, s_, reinterpret_cast<const long long*>(targets), T, h.scal, loss);
+        GRB_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (count_aside) GRB_TRY(defer_run(st, count));
     {
         LnFwdArgs a{x, ln_g, ln_b, h.xf, nullptr, h.stf, T, D, ln_eps};
         GRB_ROW_DISPATCH(D, ln_fwd_kernel, a, T, st);
     }
-    launch_k(ce_count_kernel, 1, 1024, 0, st, reinterpret_cast<const long long*>(targets), T, h.scal, loss);
-    GRB_CUDA(cudaGetLastError());
+    if (count_aside) GRB_TRY(join_pending(st));
+    else GRB_TRY(count(st));
     bool fused_dx = false;
     if (use_tc()) {
         // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly and (D <= 128) h.dxf = dlogits E

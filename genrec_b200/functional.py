@@ -113,17 +113,24 @@ class SeqMeta:
         self.ld = (L + 7) // 8 * 8
         self.bias_index = None
         self.rel32 = self.wide = None
-        dev = pad_u8.device
+        if self.pos_uniform and not attn_legacy(L):
+            self._ensure_rel()               # the tcgen05 kernels will run: they read the rebased timestamps
+        else:
+            self._build_bias_index()         # the mma.sync kernels will run: they read the index matrix
+
+    def _ensure_rel(self):
+        if self.timestamps is None or self.rel32 is not None:
+            return
+        dev = self.pad.device
+        self.rel32 = torch.empty(self.B, self.L, dtype=torch.int32, device=dev)
+        self.wide = torch.empty(self.B, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            if self.timestamps is not None:
-                self.rel32 = torch.empty(B, L, dtype=torch.int32, device=dev)
-                self.wide = torch.empty(B, dtype=torch.uint8, device=dev)
-                check(_lib.load().grb_hstu_seq_prepare(ptr(self.timestamps), ptr(self.pad), B, L, ptr(self.rel32), ptr(self.wide),
-                                                       stream_ptr(dev)))
-            if not self.pos_uniform or attn_legacy(L):
-                self._build_bias_index()
+            check(_lib.load().grb_hstu_seq_prepare(ptr(self.timestamps), ptr(self.pad), self.B, self.L, ptr(self.rel32), ptr(self.wide),
+                                                   stream_ptr(dev)))
 
     def _build_bias_index(self):
+        if self.bias_index is not None:
+            return
         B, L, dev = self.B, self.L, self.pad.device
         self.bias_index = torch.empty(B, L, self.ld, dtype=torch.int16, device=dev)
         nt = self.num_time_buckets if self.timestamps is not None else 0
@@ -134,11 +141,15 @@ class SeqMeta:
             pb_arg, npos_arg = _ZERO_TABLES[key], 1
         else:
             pb_arg, npos_arg = self.pos_bucket, self.num_pos_buckets
+        _defer_for_call(_DEFER["on"])        # deferred schedule: built on the side stream, joined before the first attention launch
         check(_lib.load().grb_hstu_bias_index(ptr(self.timestamps), ptr(self.pad), ptr(self.time_thr), ptr(pb_arg), B, L,
                                               npos_arg, nt, ptr(self.bias_index), self.ld, stream_ptr(dev)))
 
-    def struct(self) -> HstuSeq:
-        if self.bias_index is None and attn_legacy(self.L):
+    def struct(self, tc: bool = False) -> HstuSeq:
+        """tc=True: the caller will run the tcgen05 kernels whatever the dispatch policy says (stand-alone attention entry points)."""
+        if tc or (self.pos_uniform and not attn_legacy(self.L)):
+            self._ensure_rel()
+        else:
             self._build_bias_index()
         return HstuSeq(ptr(self.bias_index), self.ld, 1 if self.timestamps is not None else 0, 1 if self.pos_uniform else 0,
                        self.pos_bucket0, ptr(self.timestamps), ptr(self.pad), ptr(self.rel32), ptr(self.wide), ptr(self.time_thr))
@@ -147,7 +158,7 @@ class SeqMeta:
         """[B, L, L] uint8: the time bucket (or 64 = masked) the tcgen05 attention kernels derive for every cell (test hook)."""
         nt = self.num_time_buckets if num_time_buckets is None else num_time_buckets
         out = torch.full((self.B, self.L, self.L), 255, dtype=torch.uint8, device=self.pad.device)
-        seq = self.struct()
+        seq = self.struct(tc=True)
         with torch.cuda.device(self.pad.device):
             check(_lib.load().grb_hstu_bucket_bytes_debug(C.byref(seq), self.B, self.L, nt if self.timestamps is not None else 0, ptr(out),
                                                           stream_ptr(self.pad.device)))
@@ -378,7 +389,7 @@ def hstu_attention_fwd(P: torch.Tensor, meta: SeqMeta, H: int, pos_table: torch.
     has_time = time_table is not None and meta.timestamps is not None
     dims = _dims(B, L, D, H, pos_table.shape[0], ntime if has_time else 0, 0.0, 0, None, 0)
     O = torch.empty(B, L, D, dtype=torch.bfloat16, device=P.device)
-    seq = meta.struct()
+    seq = meta.struct(tc=True)
     with torch.cuda.device(P.device):
         check(lib.grb_hstu_attention_forward(C.byref(dims), ptr(pos_table), ptr(time_table) if has_time else None, C.byref(seq), ptr(P), ptr(O),
                                              stream_ptr(P.device)))
@@ -396,7 +407,7 @@ def hstu_attention_bwd(P, zp, dO, meta: SeqMeta, H: int, pos_table, time_table, 
     dpos = torch.zeros_like(pos_table, dtype=torch.float32)
     dtime = torch.zeros_like(time_table, dtype=torch.float32) if has_time else None
     scratch = _u8(lib.grb_hstu_attention_scratch_bytes(C.byref(dims)), P.device)
-    seq = meta.struct()
+    seq = meta.struct(tc=True)
     with torch.cuda.device(P.device):
         check(lib.grb_hstu_attention_backward(C.byref(dims), ptr(pos_table), ptr(time_table) if has_time else None, C.byref(seq), ptr(P), ptr(zp),
                                               ptr(dO), ptr(dzp), ptr(dpos), ptr(dtime), ptr(scratch), stream_ptr(P.device)))
