@@ -780,6 +780,18 @@ int grb_hstu_attention_backward(const grb_hstu_dims* d, const float* pos_table, 
                               dpos_table, dtime_table, (float*)scratch, static_cast<cudaStream_t>(stream));
 }
 
+int grb_collate_jagged(const int64_t* items, const int64_t* stamps, const int64_t* offsets, const int64_t* targets, int B, int L,
+                       int64_t* out_input_ids, int64_t* out_targets, int64_t* out_timestamps, void* stream) {
+    GRB_REQUIRE(items && offsets && targets && out_input_ids && out_targets, "null argument");
+    GRB_REQUIRE(B > 0 && L > 0, "bad shape B=%d L=%d", B, L);
+    const size_t n = (size_t)B * L;
+    launch_k(collate_jagged_kernel, (unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(items),
+             reinterpret_cast<const long long*>(stamps), reinterpret_cast<const long long*>(offsets), reinterpret_cast<const long long*>(targets), B, L,
+             reinterpret_cast<long long*>(out_input_ids), reinterpret_cast<long long*>(out_targets), reinterpret_cast<long long*>(out_timestamps));
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ embedding
 int grb_embed_forward(const int64_t* ids, const float* table, const float* pos_table, float* x, uint8_t* pad, int B, int L, int D,
                       float scale, int mask_pad_rows, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {

@@ -775,4 +775,29 @@ __global__ void __launch_bounds__(256) eval_rank_kernel(const float* __restrict_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ jagged -> left-padded batch
+// Device-side hstu_collate_fn (genrec/data/amazon_hstu.py:137-173): user b's history is items[offsets[b] .. offsets[b+1]) (time
+// order) with the held-out target targets[b].  With n = min(len_b, L) kept (the LAST n events) and pad = L - n:
+//   input_ids[b, p]  = p < pad ? 0 : hist[p - pad]          timestamps[b, p] = p < pad ? 0 : ts[p - pad]
+//   targets[b, p]    = p + 1 < pad ? 0 : (p + 1 - pad < n ? hist[p + 1 - pad] : target_b)      (the sequence shifted by one)
+// One thread per output position; stamps / out_ts may be null (SASRec: genrec/data/amazon_sasrec.py:125-161).
+__global__ void __launch_bounds__(256) collate_jagged_kernel(const long long* __restrict__ items, const long long* __restrict__ stamps,
+                                                            const long long* __restrict__ offsets, const long long* __restrict__ targets, int B,
+                                                            int L, long long* __restrict__ out_ids, long long* __restrict__ out_tg,
+                                                            long long* __restrict__ out_ts) {
+    pdl_wait();
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)B * L) return;
+    const int b = (int)(e / L), p = (int)(e % L);
+    const long long lo = offsets[b], hi = offsets[b + 1];
+    const long long len = hi - lo;
+    const int n = (int)(len < L ? len : L);
+    const int pad = L - n;
+    const long long* h = items + (hi - n);            // the last n events
+    out_ids[e] = p < pad ? 0 : h[p - pad];
+    out_tg[e] = p + 1 < pad ? 0 : (p + 1 - pad < n ? h[p + 1 - pad] : targets[b]);
+    if (out_ts != nullptr) out_ts[e] = (p < pad || stamps == nullptr) ? 0 : stamps[(hi - n) + (p - pad)];
+}
+
 }  // namespace grb

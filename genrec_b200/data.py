@@ -77,3 +77,33 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
         per = n // world
         out[k] = v[rank * per:(rank + 1) * per]
     return out
+
+
+def collate_jagged(items: torch.Tensor, offsets: torch.Tensor, targets: torch.Tensor, max_seq_len: int = 50,
+                   timestamps: "torch.Tensor | None" = None, max_len_in_batch: "int | None" = None) -> Dict[str, torch.Tensor]:
+    """hstu_collate_fn / sasrec_collate_fn ON THE DEVICE: a jagged batch that already lives in HBM (items / timestamps [N] int64 in time
+    order, offsets [B+1], one held-out target per user) -> the left-padded [B, L] batch dict, without a host round trip.
+    L = min(longest history, max_seq_len); pass ``max_len_in_batch`` (the loader knows it) to avoid the one device sync that reading it
+    from ``offsets`` costs."""
+    from . import _lib
+    from ._lib import check, ptr, require_cuda, stream_ptr
+    require_cuda(items, offsets, targets)
+    for t in (items, offsets, targets, timestamps):
+        if t is not None and t.dtype != torch.int64:
+            raise _lib.GrbError(f"genrec_b200 error -1: jagged batches are int64 (got {t.dtype})")
+    B = offsets.numel() - 1
+    if max_len_in_batch is None:
+        max_len_in_batch = int((offsets[1:] - offsets[:-1]).max().item())
+    L = max(1, min(int(max_len_in_batch), int(max_seq_len)))
+    dev = items.device
+    ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+    tgs = torch.empty(B, L, dtype=torch.int64, device=dev)
+    tss = torch.empty(B, L, dtype=torch.int64, device=dev) if timestamps is not None else None
+    with torch.cuda.device(dev):
+        check(_lib.load().grb_collate_jagged(ptr(items.contiguous()), ptr(timestamps.contiguous()) if timestamps is not None else None,
+                                             ptr(offsets.contiguous()), ptr(targets.contiguous()), B, L, ptr(ids), ptr(tgs), ptr(tss),
+                                             stream_ptr(dev)))
+    out = {"input_ids": ids, "targets": tgs}
+    if tss is not None:
+        out["timestamps"] = tss
+    return out

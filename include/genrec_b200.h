@@ -130,6 +130,14 @@ int grb_hstu_layer_backward(const grb_hstu_dims* d, const grb_hstu_layer_params*
                             const float* dy, const void* saved, float* dx, const grb_hstu_layer_grads* g,
                             void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ input pipeline
+ * Device-side hstu_collate_fn / sasrec_collate_fn (genrec/data/amazon_hstu.py:137-173, genrec/data/amazon_sasrec.py:125-161): a
+ * jagged batch (items / stamps [N] in time order, offsets [B+1], one held-out target per user) -> the LEFT-padded [B, L]
+ * input_ids / targets (inputs shifted by one) / timestamps the models consume.  L = min(longest history of the batch, max_seq_len)
+ * is chosen by the caller, who knows the lengths when it forms the batch.  stamps / out_timestamps may be NULL. */
+int grb_collate_jagged(const int64_t* items, const int64_t* stamps, const int64_t* offsets, const int64_t* targets, int B, int L,
+                       int64_t* out_input_ids, int64_t* out_targets, int64_t* out_timestamps, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ embedding gather
  * Replaces item_embedding + emb_dropout (hstu.py:124-128) / the scaled item+position embedding of SASRec
  * (sasrec.py:100-111).  pos_table may be NULL; mask_pad_rows multiplies rows whose id is 0 by zero (SASRec). */

@@ -50,14 +50,14 @@ def position_bias(table: torch.Tensor, L: int, num_buckets: int = 32, max_distan
     pos = torch.arange(L, device=table.device)
     rel = pos.unsqueeze(0) - pos.unsqueeze(1)                    # [i, j] = j - i
     bkt = position_bucket(rel, num_buckets, max_distance)
-    return table[bkt].permute(2, 0, 1)                           # [H, L, L]
+    return F.embedding(bkt, table).permute(2, 0, 1)              # [H, L, L]   (nn.Embedding lookup, hstu.py:346-347)
 
 
 def temporal_bias(table: torch.Tensor, timestamps: torch.Tensor) -> torch.Tensor:
     """[B, H, L, L] bias.  Follows genrec/models/hstu.py:386-409."""
     diff = timestamps.unsqueeze(2) - timestamps.unsqueeze(1)     # [b,i,j] = ts_i - ts_j  (:400)
     bkt = temporal_bucket(diff, table.shape[0])
-    return table[bkt].permute(0, 3, 1, 2)                        # (:406-407)
+    return F.embedding(bkt, table).permute(0, 3, 1, 2)           # nn.Embedding lookup (:406-407)
 
 
 # --------------------------------------------------------------------------- layer

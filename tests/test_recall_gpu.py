@@ -108,3 +108,31 @@ def test_device_side_metrics_match_the_trainer_loop():
     assert ranks.tolist() == [2, 1, 0]
     torch.testing.assert_close(met.cpu(), torch.tensor([1.0, 2.0, 2.0, 1.0, 1.0 + 1 / torch.log2(torch.tensor(3.0)).item(),
                                                         1.0 + 1 / torch.log2(torch.tensor(3.0)).item()]))
+
+
+def test_device_collate_equals_reference_collate():
+    """grb_collate_jagged (jagged batch in HBM -> left-padded ids / targets / timestamps) == hstu_collate_fn / sasrec_collate_fn on the
+    same samples (whose mirrors are pinned to the reference's own collate output in tests/test_modules_cpu.py)."""
+    from genrec_b200.data import collate_jagged, hstu_collate_fn, sasrec_collate_fn
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    for max_seq_len in (50, 7):
+        lens = torch.randint(1, 30, (33,), generator=g).tolist()
+        batch = []
+        for n in lens:
+            ts = (1_300_000_000 + torch.cumsum(torch.randint(1, 10 ** 5, (n,), generator=g), 0)).tolist()
+            batch.append(dict(history=torch.randint(1, 1000, (n,), generator=g).tolist(), timestamps=ts,
+                              target=int(torch.randint(1, 1000, (1,), generator=g))))
+        want = hstu_collate_fn(batch, max_seq_len)
+        items = torch.tensor([v for b in batch for v in b["history"]], device=dev)
+        stamps = torch.tensor([v for b in batch for v in b["timestamps"]], device=dev)
+        offsets = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), device=dev)
+        targets = torch.tensor([b["target"] for b in batch], device=dev)
+        got = collate_jagged(items, offsets, targets, max_seq_len, timestamps=stamps)
+        for k in ("input_ids", "targets", "timestamps"):
+            assert torch.equal(got[k].cpu(), want[k]), (max_seq_len, k)
+        got = collate_jagged(items, offsets, targets, max_seq_len, max_len_in_batch=max(lens))
+        want = sasrec_collate_fn([dict(history=b["history"], target=b["target"]) for b in batch], max_seq_len)
+        assert "timestamps" not in got
+        for k in ("input_ids", "targets"):
+            assert torch.equal(got[k].cpu(), want[k]), (max_seq_len, k)
