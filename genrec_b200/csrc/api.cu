@@ -819,6 +819,7 @@ int grb_embed_backward(const int64_t* ids, const float* dx, float* dtable, float
 namespace {
 struct HeadWork {
     bf16* xf; float* stf; bf16* logits; float* dxf; float* scal;  // scal[0] = inv_count
+    bf16* xs; float* row_sums; float2* row_stats;                  // fused CE: x / sum_row, per-row sums of G', {max, target logit}
     void* ce_scratch;
     int ldl;
     size_t bytes;
@@ -833,6 +834,9 @@ HeadWork carve_head(void* base, size_t T, size_t D, size_t C) {
     h.stf = (float*)take(T * 2 * 4);
     h.dxf = (float*)take(T * D * 4);
     h.scal = (float*)take(64);
+    h.xs = (bf16*)take(T * D * 2);
+    h.row_sums = (float*)take(2 * T * 4);
+    h.row_stats = (float2*)take(T * 8);
     h.ce_scratch = take(ce_scratch_bytes((int)T));
     h.logits = (bf16*)take(T * (size_t)h.ldl * 2);
     h.bytes = off;
@@ -870,9 +874,9 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     if (use_tc()) {
         // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly and (D <= 128) h.dxf = dlogits E
         const long long* tg = reinterpret_cast<const long long*>(targets);                                  // (hstu.py:137-146)
-        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, loss, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)
@@ -881,13 +885,22 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         launch_k(ce_fwd_bwd_kernel, T, 256, 0, st, h.logits, h.ldl, C, reinterpret_cast<const long long*>(targets), h.scal, loss, want_grad ? 1 : 0);
     GRB_CUDA(cudaGetLastError());
     }
+    if (use_tc()) {
+        // normalisation pass of the fused CE (rowwise.cuh ce_finish_kernel): loss, and - with gradients - dxf, x / sum_row, the one-hot
+        // term of dE.  Without the dX fusion (D = 256) dxf' = G' E comes from a GEMM first.
+        if (want_grad && !fused_dx) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));
+        CeFinishArgs fa{h.row_sums, h.row_stats, reinterpret_cast<const long long*>(targets), h.scal, h.xf, (const bf16*)table_bf16,
+                        want_grad ? h.dxf : nullptr, want_grad ? h.xs : nullptr, want_grad ? dtable : nullptr, loss, T, D};
+        launch_k(ce_finish_kernel, row_grid(T), ROW_THREADS, 0, st, fa);
+        GRB_CUDA(cudaGetLastError());
+    }
     if (!want_grad) return 0;
     {
-        if (!fused_dx) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
+        if (!use_tc()) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
     }
     {
         if (use_tc()) {
-            TnSpec spec{h.logits, h.xf, dtable, C, D, T, h.ldl, D, D};  // dE[C,D] += dlogits^T xf
+            TnSpec spec{h.logits, h.xs, dtable, C, D, T, h.ldl, D, D};  // dE[C,D] += G'^T (xf / sum_row) = dlogits^T xf
             if (g_defer_on) {
                 GRB_TRY(defer_run(st, [&](cudaStream_t side) -> int {
                     GRB_CUDA(launch_tc_tn_group(&spec, 1, sm_count(), side));

@@ -800,4 +800,71 @@ __global__ void __launch_bounds__(256) collate_jagged_kernel(const long long* __
     if (out_ts != nullptr) out_ts[e] = (p < pad || stamps == nullptr) ? 0 : stamps[(hi - n) + (p - pad)];
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused CE: normalisation pass
+// The fused CE kernel (tc_ce.cuh) leaves G' = exp(s - max) / count unnormalised and reports, per row, the sum of G' over each
+// class half, the row max and the target logit.  With rs = 1 / sum_c exp(s_c - max) (so that G = G' rs is the softmax / count):
+//   loss    += (max + log sum exp - logit[target]) / count
+//   dxf      = dxf' rs - E[target] / count                 (dxf' = G' E from the CE kernel or the GEMM)
+//   xs       = bf16(x rs)                                   -> the dE GEMM computes G'^T xs = G^T x
+//   dE[target] -= x / count                                 (the one-hot term of dE, a 16-byte-vector scatter)
+// One warp per token row; rows with target 0 (ignore_index) get rs = 0 and contribute nothing.
+struct CeFinishArgs {
+    const float* row_sums;       // [2][T]
+    const float2* row_stats;     // [T] {max, target logit}
+    const long long* targets;    // [T]
+    const float* inv_count;
+    const bf16* xf;              // [T, D]
+    const bf16* table;           // [C, D] bf16 mirror of the tied embedding table
+    float* dxf;                  // [T, D] in: G' E, out: d loss / d xf   (nullable: loss only)
+    bf16* xs;                    // [T, D] out (nullable)
+    float* dtable;               // [C, D] += (nullable)
+    float* loss;                 // += (zeroed by ce_count_kernel)
+    int T, D;
+};
+__global__ void __launch_bounds__(ROW_THREADS) ce_finish_kernel(CeFinishArgs a) {
+    pdl_wait();
+    __shared__ float s_loss[ROW_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpb = ROW_THREADS / 32;
+    const float ic = *a.inv_count;
+    float lsum = 0.f;
+    for (int row = blockIdx.x * wpb + warp; row < a.T; row += gridDim.x * wpb) {
+        const int t = (int)a.targets[row];
+        const float icr = t != 0 ? ic : 0.f;
+        const float gs = a.row_sums[row] + a.row_sums[(size_t)a.T + row];        // = sum_c exp(s_c - max) * icr
+        const float rs = (icr > 0.f && gs > 0.f) ? icr / gs : 0.f;                // 1 / sum_c exp(s_c - max)
+        if (lane == 0 && icr > 0.f) {
+            const float2 st = a.row_stats[row];
+            lsum += (st.x + __logf(gs / icr) - st.y) * icr;
+        }
+        const bf16* x = a.xf + (size_t)row * a.D;
+        const bf16* e = a.table + (size_t)t * a.D;
+        for (int c = lane * 4; c < a.D; c += 128) {
+            const uint2 xu = *reinterpret_cast<const uint2*>(x + c);
+            const float2 x0 = unpack_bf16(xu.x), x1 = unpack_bf16(xu.y);
+            if (a.xs) {
+                uint2 o;
+                o.x = pack_bf16(x0.x * rs, x0.y * rs); o.y = pack_bf16(x1.x * rs, x1.y * rs);
+                *reinterpret_cast<uint2*>(a.xs + (size_t)row * a.D + c) = o;
+            }
+            if (a.dxf) {
+                float4 d = *reinterpret_cast<float4*>(a.dxf + (size_t)row * a.D + c);
+                const uint2 eu = *reinterpret_cast<const uint2*>(e + c);
+                const float2 e0 = unpack_bf16(eu.x), e1 = unpack_bf16(eu.y);
+                d.x = d.x * rs - icr * e0.x; d.y = d.y * rs - icr * e0.y; d.z = d.z * rs - icr * e1.x; d.w = d.w * rs - icr * e1.y;
+                *reinterpret_cast<float4*>(a.dxf + (size_t)row * a.D + c) = d;
+            }
+            if (a.dtable && icr > 0.f) red_add_v4(a.dtable + (size_t)t * a.D + c, -icr * x0.x, -icr * x0.y, -icr * x1.x, -icr * x1.y);
+        }
+    }
+    if (lane == 0) s_loss[warp] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < wpb; ++w) tot += s_loss[w];
+        if (tot != 0.f) atomicAdd(a.loss, tot);
+    }
+}
+
 }  // namespace grb

@@ -4,8 +4,12 @@
 // autograd softmax-backward and the `dlogits @ E` GEMM.  The [T, C] logits tensor is never written: one CTA owns a block
 // of 128 token rows (token tile resident in shared memory) and sweeps the C classes twice with the same TMA -> tcgen05.mma
 // pipeline, the embedding table streaming from L2:
-//   sweep 0 : S = X E_n^T in TMEM  ->  per-row running (max, sum exp) + the target logit, one thread per (row, 32 columns)
-//   sweep 1 : S recomputed         ->  G = (exp(S - lse) - onehot(target)) * inv_count  ->  bf16, 128B-swizzled staging tile
+//   sweep 0 : S = X E_n^T in TMEM  ->  per-row running MAX + the target logit, one thread per (row, 32 columns) - no exponentials
+//   sweep 1 : S recomputed         ->  G' = exp(S - max) * inv_count (UNNORMALISED: the row sum is only known once this sweep
+//                                      has seen every class) + the row sum  ->  bf16, 128B-swizzled staging tile
+//   Every logit therefore costs ONE exponential (the kernel is MUFU-bound: the first version spent one per sweep).  The
+//   normalisation 1 / sum_row commutes with both products that consume G': ce_finish_kernel scales dX' = G' E by it, subtracts the
+//   one-hot term, and hands the dE GEMM x / sum_row instead of x.
 //                                      -> TMA store to dlogits (consumed by the dE = G^T X GEMM)
 //                                      -> (D <= 128) the SAME staging tile is the K-major A operand of a second MMA
 //                                         dX[128, D] += G_tile E_n, whose B operand is the E_n tile already in shared memory
@@ -51,7 +55,9 @@ GRB_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
 template <int KB>  // k-blocks of 64: D = 64 * KB
 __global__ void __launch_bounds__(CE_THREADS, 1)
     tc_ce_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmG,
-                 CeShape sh, const long long* __restrict__ targets, const float* __restrict__ inv_count, float* __restrict__ loss,
+                 CeShape sh, const long long* __restrict__ targets, const float* __restrict__ inv_count,
+                 float* __restrict__ row_sums /* [2][T]: sum_c G'[row, c] of each class half */,
+                 float2* __restrict__ row_stats /* [T]: {row max, target logit} */,
                  float* __restrict__ dx_out /* [T, 64*KB] fp32, written only when the dX fusion is compiled in (KB <= 2) */) {
     constexpr bool FUSE_DX = KB <= 2;
     constexpr int NS = KB <= 2 ? 3 * KB : 5;
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             const int row = blk * 128 + r;
             const int t = row < sh.T ? (int)targets[row] : 0;
             const float icr = t != 0 ? ic : 0.f;   // ignore_index = 0 (and rows past the end)
-            float m_run = -INFINITY, s_run = 0.f, tl = 0.f;
+            float m_run = -INFINITY, tl = 0.f;
             // ------------------------------------------------------------------ sweep 0: statistics
             for (int n = nb; n < ne; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
@@ -241,35 +247,23 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     float cm = v[0];
 #pragma unroll
                     for (int i = 1; i < 32; ++i) cm = fmaxf(cm, v[i]);
-                    const float m_new = fmaxf(m_run, cm);
-                    if (m_new > -INFINITY) {
-                        float cs = 0.f;
-                        const float m2 = m_new * kLog2e;   // exp(v - m) = 2^(v * log2e - m * log2e): one FFMA + one MUFU per logit
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) cs += ex2_fast(fmaf(v[i], kLog2e, -m2));
-                        s_run = s_run * __expf(m_run - m_new) + cs;
-                        m_run = m_new;
-                    }
+                    m_run = fmaxf(m_run, cm);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             // combine the four column quarters of every row (this half of the classes) ...
             s_part[(cq * 3 + 0) * 128 + r] = m_run;
-            s_part[(cq * 3 + 1) * 128 + r] = s_run;
             s_part[(cq * 3 + 2) * 128 + r] = tl;
             ce_bar_sync();
-            float mh = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mh = fmaxf(mh, s_part[(q * 3 + 0) * 128 + r]);
-            float sh_ = 0.f, tlh = 0.f;
+            float mh = -INFINITY, tlh = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float mq = s_part[(q * 3 + 0) * 128 + r];
-                sh_ += (mq == -INFINITY) ? 0.f : s_part[(q * 3 + 1) * 128 + r] * __expf(mq - mh);
+                mh = fmaxf(mh, s_part[(q * 3 + 0) * 128 + r]);
                 tlh += s_part[(q * 3 + 2) * 128 + r];
             }
-            // ... publish them, and pick up the partner item's partials for the other half of the classes
-            if (cq == 0) sh.stats[(size_t)w * 128 + r] = make_float4(mh, sh_, tlh, 0.f);
+            // ... publish them, and pick up the partner item's maximum: both halves must scale their exponentials alike, their dX'
+            // partials and G' tiles are summed
+            if (cq == 0) sh.stats[(size_t)w * 128 + r] = make_float4(mh, 0.f, tlh, 0.f);
             __threadfence();
             ce_bar_sync();
             if (warp == 2 && lane == 0) {
@@ -279,13 +273,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             ce_bar_sync();
             const float4 pp = __ldcg(sh.stats + (size_t)(w ^ 1) * 128 + r);
             const float mm = fmaxf(mh, pp.x);
-            const float ssum = ((mh == -INFINITY) ? 0.f : sh_ * __expf(mh - mm)) + ((pp.x == -INFINITY) ? 0.f : pp.y * __expf(pp.x - mm));
-            const float lse = mm + __logf(ssum);
-            const float gshift = lse * kLog2e - __log2f(icr);   // icr == 0 (ignored row) -> +inf -> every gradient entry is 2^-inf = 0
-            // loss: half 0 / quarter 0 adds lse - logit[target] once per row
-            float contrib = (half == 0 && cq == 0) ? (lse - (tlh + pp.z)) * icr : 0.f;
-            contrib = warp_sum(contrib);
-            if (lane == 0 && contrib != 0.f) atomicAdd(loss, contrib);
+            const float gshift = mm * kLog2e - __log2f(icr);   // icr == 0 (ignored row) -> +inf -> every entry of G' is 2^-inf = 0
+            if (half == 0 && cq == 0 && row < sh.T) row_stats[row] = make_float2(mm, tlh + pp.z);
+            float g_sum = 0.f;                                 // sum of this thread's G' entries (this half, this quarter)
             // ------------------------------------------------------------------ sweep 1: gradient tiles
             if (warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
             ce_bar_sync();                                     // (also: everybody has read s_part)
@@ -302,16 +292,17 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained (it lives in registers now)
                     const int col0 = n * 128 + cq * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // softmax * (1/count), folded into the exponent
+                    for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // exp(s - max) * (1/count), folded into the exponent
                     if (col0 + 32 > sh.C) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (col0 + i >= sh.C) v[i] = 0.f;
                     }
-                    if ((unsigned)(t - col0) < 32u) {
+                    {   // row sum of G' (four partial chains keep the adds off the critical path)
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i == t - col0) v[i] -= icr;
+                        for (int i = 0; i < 32; i += 4) { a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3]; }
+                        g_sum += (a0 + a1) + (a2 + a3);
                     }
                     unsigned char* dst = sOut + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -337,8 +328,13 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 if (gbuf == 1) gphase ^= 1;
                 gbuf ^= 1;
             }
+            // row sums of this half -> global (four quarters combined through shared memory; slot 1 of s_part is free now)
+            s_part[(cq * 3 + 1) * 128 + r] = g_sum;
+            ce_bar_sync();
+            if (cq == 0 && row < sh.T)
+                row_sums[(size_t)half * sh.T + row] = (s_part[1 * 128 + r] + s_part[4 * 128 + r]) + (s_part[7 * 128 + r] + s_part[10 * 128 + r]);
             if (FUSE_DX && ne > nb) {
-                // ------------------------------------------------------------------ dX partial of this half: TMEM -> += fp32 global
+                // ------------------------------------------------------------------ dX' partial of this half: TMEM -> += fp32 global
                 mbar_wait(dxfull, dxphase);
                 dxphase ^= 1;
                 tc_fence_after();
@@ -366,13 +362,14 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     }
 }
 
-// X [T, D] bf16, E [C, D] bf16 -> G [T, ldl] bf16 (columns >= C zeroed), loss += sum_rows(lse - logit[target]) * inv_count,
-// and (D <= 128) dx [T, D] fp32 = G E.  Returns through *fused_dx whether dx was produced.
+// X [T, D] bf16, E [C, D] bf16 -> G' [T, ldl] bf16 = exp(s - rowmax) * inv_count (columns >= C zeroed), row_sums [2][T], row_stats [T]
+// {max, target logit}, and (D <= 128) dx' [T, D] fp32 = G' E.  Returns through *fused_dx whether dx' was produced.  ce_finish_kernel
+// (rowwise.cuh) turns these into the loss, d loss / d x and the operand of the dE GEMM.
 inline size_t ce_scratch_bytes(int T) { return (size_t)2 * ((T + 127) / 128) * (128 * sizeof(float4) + sizeof(unsigned)) + 256; }
 // scratch: ce_scratch_bytes(T) bytes of device memory (partials + flags); dx must hold [T, D] fp32 and is zero-filled here
 template <int KB>
 inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, int C, int ldl, const long long* targets, const float* inv_count,
-                                float* loss, float* dx, bool* fused_dx, void* scratch, int num_sms, cudaStream_t st) {
+                                float* row_sums, float2* row_stats, float* dx, bool* fused_dx, void* scratch, int num_sms, cudaStream_t st) {
     CUtensorMap tmX, tmE, tmG;
     const int D = 64 * KB;
     bool ok = make_tmap_bf16(&tmX, X, T, D, D, 64, 128) && make_tmap_bf16(&tmE, E, C, D, D, 64, 128) && make_tmap(&tmG, G, false, T, ldl, ldl, 64, 128);
@@ -403,7 +400,7 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
     }
     // the two halves of a row block spin on each other: both must be resident at the same time -> even, persistent grid
     int grid = 2 * sh.num_m < num_sms ? 2 * sh.num_m : (num_sms & ~1);
-    launch_k(kern, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, loss, dx);
+    launch_k(kern, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums, row_stats, dx);
     return cudaGetLastError();
 }
 
