@@ -70,6 +70,10 @@ int sm_count() {     // per device ordinal: a process may drive several GPUs
     }
     return n[dev];
 }
+bool ce_store_forced() {
+    static const bool v = [] { const char* e = getenv("GRB_CE"); return e && !strcmp(e, "store"); }();
+    return v;
+}
 int row_grid(int T) {
     int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
     int cap = sm_count() * 8;
@@ -820,6 +824,7 @@ namespace {
 struct HeadWork {
     bf16* xf; float* stf; bf16* logits; float* dxf; float* scal;  // scal[0] = inv_count
     bf16* xs; float* row_sums; float2* row_stats;                  // fused CE: x / sum_row, per-row sums of G', {max, target logit}
+    float* col_shift;                                              // fused CE: exponent shift of every token for the class-stationary dE pass
     void* ce_scratch;
     int ldl;
     size_t bytes;
@@ -837,6 +842,7 @@ HeadWork carve_head(void* base, size_t T, size_t D, size_t C) {
     h.xs = (bf16*)take(T * D * 2);
     h.row_sums = (float*)take(2 * T * 4);
     h.row_stats = (float2*)take(T * 8);
+    h.col_shift = (float*)take(((T + 127) / 128) * 128 * 4);
     h.ce_scratch = take(ce_scratch_bytes((int)T));
     h.logits = (bf16*)take(T * (size_t)h.ldl * 2);
     h.bytes = off;
@@ -871,12 +877,16 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     if (count_aside) GRB_TRY(join_pending(st));
     else GRB_TRY(count(st));
     bool fused_dx = false;
+    // D <= 128: no [T, C] tensor reaches HBM - dX' accumulates in TMEM beside the CE sweep and dE comes from a class-stationary pass
+    // that recomputes G (GRB_CE=store keeps the round-1 schedule: G' stored, dE by the TN GEMM).  D = 256: G' is stored.
+    const bool keep_g = use_tc() && D <= 128 && want_grad && !ce_store_forced();
     if (use_tc()) {
-        // fused: logits are never materialised; h.logits receives d(loss)/d(logits) directly and (D <= 128) h.dxf = dlogits E
+        // fused: logits are never materialised; (D <= 128) h.dxf = G' E, and h.logits receives G' only when a dE GEMM needs it
         const long long* tg = reinterpret_cast<const long long*>(targets);                                  // (hstu.py:137-146)
-        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else GRB_CUDA(launch_tc_ce<4>(h.xf, (const bf16*)table_bf16, h.logits, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        const bf16* tb = (const bf16*)table_bf16;
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, tb, h.logits, !keep_g, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, tb, h.logits, !keep_g, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, tb, h.logits, true, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)
@@ -890,7 +900,8 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         // term of dE.  Without the dX fusion (D = 256) dxf' = G' E comes from a GEMM first.
         if (want_grad && !fused_dx) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));
         CeFinishArgs fa{h.row_sums, h.row_stats, reinterpret_cast<const long long*>(targets), h.scal, h.xf, (const bf16*)table_bf16,
-                        want_grad ? h.dxf : nullptr, want_grad ? h.xs : nullptr, want_grad ? dtable : nullptr, loss, T, D};
+                        want_grad ? h.dxf : nullptr, (want_grad && !keep_g) ? h.xs : nullptr, keep_g ? h.col_shift : nullptr,
+                        want_grad ? dtable : nullptr, loss, T, D};
         launch_k(ce_finish_kernel, row_grid(T), ROW_THREADS, 0, st, fa);
         GRB_CUDA(cudaGetLastError());
     }
@@ -899,7 +910,17 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         if (!use_tc()) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));  // dxf = dlogits E
     }
     {
-        if (use_tc()) {
+        if (keep_g) {
+            // dE[C,D] += G^T xf with G recomputed class block by class block (tc_ce.cuh CE_ACCUM_T); off the critical path like the
+            // other weight gradients
+            auto accum = [&](cudaStream_t s_) -> int {
+                if (D == 64) GRB_CUDA(launch_tc_ce_accum_t<1>(h.xf, (const bf16*)table_bf16, h.col_shift, dtable, T, C, sm_count(), s_));
+                else GRB_CUDA(launch_tc_ce_accum_t<2>(h.xf, (const bf16*)table_bf16, h.col_shift, dtable, T, C, sm_count(), s_));
+                return 0;
+            };
+            if (g_defer_on) GRB_TRY(defer_run(st, accum));
+            else GRB_TRY(accum(st));
+        } else if (use_tc()) {
             TnSpec spec{h.logits, h.xs, dtable, C, D, T, h.ldl, D, D};  // dE[C,D] += G'^T (xf / sum_row) = dlogits^T xf
             if (g_defer_on) {
                 GRB_TRY(defer_run(st, [&](cudaStream_t side) -> int {

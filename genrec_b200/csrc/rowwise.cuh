@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(EmbedBwdArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------ cross entropy on bf16 logits
-// count = #(targets != 0)  -> inv_count (0 if none)
+// count = #(targets != 0)  -> inv_count (0 if none); loss <- 0, or NaN when no target is valid (F.cross_entropy's 0 / 0 mean,
+// hstu.py:141-146; the gradients of such a batch are zero here, NaN in the reference)
 __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* __restrict__ inv_count, float* __restrict__ loss) {
     pdl_wait();
     __shared__ int red[32];
@@ -505,7 +506,7 @@ __global__ void ce_count_kernel(const long long* __restrict__ tg, int T, float* 
         int s = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
         *inv_count = s > 0 ? 1.f / (float)s : 0.f;
-        *loss = 0.f;
+        *loss = s > 0 ? 0.f : __int_as_float(0x7fc00000);
     }
 }
 // one CTA per row: loss += (lse - logit[target]) * inv_count ; logits <- (softmax - onehot) * inv_count  (0 for ignored rows)
@@ -806,7 +807,8 @@ __global__ void __launch_bounds__(256) collate_jagged_kernel(const long long* __
 // class half, the row max and the target logit.  With rs = 1 / sum_c exp(s_c - max) (so that G = G' rs is the softmax / count):
 //   loss    += (max + log sum exp - logit[target]) / count
 //   dxf      = dxf' rs - E[target] / count                 (dxf' = G' E from the CE kernel or the GEMM)
-//   xs       = bf16(x rs)                                   -> the dE GEMM computes G'^T xs = G^T x
+//   xs       = bf16(x rs)                                   -> a dE GEMM over the stored G' computes G'^T xs = G^T x, or
+//   col_shift = log2e * logsumexp - log2(1 / count)         -> the class-stationary pass (tc_ce.cuh CE_ACCUM_T) recomputes G from it
 //   dE[target] -= x / count                                 (the one-hot term of dE, a 16-byte-vector scatter)
 // One warp per token row; rows with target 0 (ignore_index) get rs = 0 and contribute nothing.
 struct CeFinishArgs {
@@ -818,6 +820,7 @@ struct CeFinishArgs {
     const bf16* table;           // [C, D] bf16 mirror of the tied embedding table
     float* dxf;                  // [T, D] in: G' E, out: d loss / d xf   (nullable: loss only)
     bf16* xs;                    // [T, D] out (nullable)
+    float* col_shift;            // [ceil(T / 128) * 128] out (nullable); +inf for ignored rows and the padding
     float* dtable;               // [C, D] += (nullable)
     float* loss;                 // += (zeroed by ce_count_kernel)
     int T, D;
@@ -834,9 +837,11 @@ __global__ void __launch_bounds__(ROW_THREADS) ce_finish_kernel(CeFinishArgs a) 
         const float icr = t != 0 ? ic : 0.f;
         const float gs = a.row_sums[row] + a.row_sums[(size_t)a.T + row];        // = sum_c exp(s_c - max) * icr
         const float rs = (icr > 0.f && gs > 0.f) ? icr / gs : 0.f;                // 1 / sum_c exp(s_c - max)
-        if (lane == 0 && icr > 0.f) {
+        if (lane == 0) {
             const float2 st = a.row_stats[row];
-            lsum += (st.x + __logf(gs / icr) - st.y) * icr;
+            const bool live = icr > 0.f && gs > 0.f;
+            if (live) lsum += (st.x + __logf(gs / icr) - st.y) * icr;
+            if (a.col_shift) a.col_shift[row] = live ? st.x * 1.4426950408889634f + __log2f(gs / icr) - __log2f(icr) : INFINITY;
         }
         const bf16* x = a.xf + (size_t)row * a.D;
         const bf16* e = a.table + (size_t)t * a.D;
@@ -858,6 +863,8 @@ __global__ void __launch_bounds__(ROW_THREADS) ce_finish_kernel(CeFinishArgs a) 
             if (a.dtable && icr > 0.f) red_add_v4(a.dtable + (size_t)t * a.D + c, -icr * x0.x, -icr * x0.y, -icr * x1.x, -icr * x1.y);
         }
     }
+    if (a.col_shift && blockIdx.x == 0)
+        for (int i = a.T + threadIdx.x; i < ((a.T + 127) / 128) * 128; i += ROW_THREADS) a.col_shift[i] = INFINITY;
     if (lane == 0) s_loss[warp] = lsum;
     __syncthreads();
     if (threadIdx.x == 0) {

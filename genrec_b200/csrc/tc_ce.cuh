@@ -35,15 +35,41 @@ constexpr int ce_smem_bytes() {   // fused dX (KB <= 2) keeps the table slices o
     return KB * TC_TILE_BYTES + (KB <= 2 ? 3 * KB : 5) * TC_TILE_BYTES + 2 * 32768 + 12 * 128 * 4 + 1024 + 256;
 }
 
+// Kernel modes.  CE_STORE_G and CE_KEEP_G are the row-stationary CE pass (token rows resident, classes streaming) with / without the
+// bf16 G' tile going to HBM; CE_ACCUM_T is the same pipeline with the operands exchanged (a block of 128 CLASS rows resident, the token
+// tiles streaming, the exponent shift a per-COLUMN array): its "dX" accumulator is dE[class, :] = sum_tokens G[token, class] x[token, :],
+// so the tied-table gradient needs no [T, C] tensor in HBM either - it recomputes S once more instead (K = D is cheap).
+enum { CE_STORE_G = 0, CE_KEEP_G = 1, CE_ACCUM_T = 2 };
+
 struct CeShape {
-    int T, C, ldl;       // tokens, classes, leading dimension of dlogits (multiple of 8, >= C)
+    int T, C, ldl;       // rows of the resident operand, rows of the streaming operand, leading dimension of dlogits (multiple of 8, >= C)
     int num_m, num_n;
     int n_half;          // class tiles [0, n_half) belong to half 0, [n_half, num_n) to half 1
+    int nsplit;          // CE_ACCUM_T: work items per resident block (each sweeps 1/nsplit of the streaming tiles); 2 otherwise
     float4* stats;       // [2 * num_m][128] {max, sum, target logit, -}  partials published after sweep 0
     unsigned* flags;     // [2 * num_m] zero before launch
 };
 GRB_DEVINL void red_add_v4_ce(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive bf16 along K)
+GRB_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+GRB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 GRB_DEVINL void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 GRB_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
@@ -52,14 +78,31 @@ GRB_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-template <int KB>  // k-blocks of 64: D = 64 * KB
+template <int MODE>
+GRB_DEVINL void ce_item(int w, const CeShape& sh, int& blk, int& nb, int& ne) {
+    if (MODE == CE_ACCUM_T) {
+        blk = w / sh.nsplit;
+        const int p = w - blk * sh.nsplit;
+        nb = (int)((long long)p * sh.num_n / sh.nsplit);
+        ne = (int)((long long)(p + 1) * sh.num_n / sh.nsplit);
+    } else {
+        blk = w >> 1;
+        nb = (w & 1) ? sh.n_half : 0;
+        ne = (w & 1) ? sh.num_n : sh.n_half;
+    }
+}
+
+template <int KB, int MODE>  // k-blocks of 64: D = 64 * KB
 __global__ void __launch_bounds__(CE_THREADS, 1)
     tc_ce_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmG,
                  CeShape sh, const long long* __restrict__ targets, const float* __restrict__ inv_count,
                  float* __restrict__ row_sums /* [2][T]: sum_c G'[row, c] of each class half */,
                  float2* __restrict__ row_stats /* [T]: {row max, target logit} */,
-                 float* __restrict__ dx_out /* [T, 64*KB] fp32, written only when the dX fusion is compiled in (KB <= 2) */) {
+                 const float* __restrict__ col_shift /* CE_ACCUM_T: [num_n * 128] exponent shift of each streaming row (+inf = skip) */,
+                 float* __restrict__ dx_out /* [T, 64*KB] fp32 +=, written only when the second MMA is compiled in (KB <= 2) */) {
     constexpr bool FUSE_DX = KB <= 2;
+    static_assert(MODE == CE_STORE_G || FUSE_DX, "without the G' store the second MMA is the only consumer of the tile");
+    constexpr int SWEEPS = MODE == CE_ACCUM_T ? 1 : 2;
     constexpr int NS = KB <= 2 ? 3 * KB : 5;
     constexpr int D = 64 * KB;
     extern __shared__ unsigned char ce_smem_raw[];
@@ -85,11 +128,11 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmE);
-        tma_prefetch_desc(&tmG);
+        if (MODE == CE_STORE_G) tma_prefetch_desc(&tmG);
         for (int s = 0; s < NS; ++s) { mbar_init(&efull[s], 1); mbar_init(&eempty[s], 1); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CE_EPI_WARPS);
-            mbar_init(&gfull[a], 1); mbar_init(&gempty[a], 1);
+            mbar_init(&gfull[a], MODE == CE_STORE_G ? 1 : CE_EPI_WARPS); mbar_init(&gempty[a], 1);
         }
         mbar_init(xfull, 1);
         mbar_init(xempty, 1);
@@ -104,21 +147,25 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // prologue above overlaps the previous kernel's tail
     const uint32_t tmem_dx = tmem_base + 256;
-    const int num_items = 2 * sh.num_m;
+    // CE_KEEP_G / CE_ACCUM_T: the G tile never touches shared memory - the epilogue packs it to bf16 pairs in tensor memory (2 x 64
+    // columns) and the second MMA takes its A operand from there.  With both operands in shared memory that MMA alone would read
+    // 96 KB per class tile (two N = 64 instructions re-reading A); the kernel is bound by shared-memory bandwidth, not by the tensor pipe.
+    const uint32_t tmem_g = tmem_base + 384;
+    const int num_items = (MODE == CE_ACCUM_T ? sh.nsplit : 2) * sh.num_m;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, xphase = 0;
             for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-                const int blk = w >> 1;
-                const int nb = (w & 1) ? sh.n_half : 0, ne = (w & 1) ? sh.num_n : sh.n_half;
+                int blk, nb, ne;
+                ce_item<MODE>(w, sh, blk, nb, ne);
                 const int ntile = ne - nb;
                 mbar_wait(xempty, xphase ^ 1);
                 mbar_expect_tx(xfull, KB * TC_TILE_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(sX + kb * TC_TILE_BYTES, &tmX, kb * 64, blk * 128, xfull);
                 xphase ^= 1;
-                for (int tile = 0; tile < 2 * ntile; ++tile) {
+                for (int tile = 0; tile < SWEEPS * ntile; ++tile) {
                     const int n0 = (nb + tile % ntile) * 128;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&eempty[stage], phase ^ 1);
@@ -139,6 +186,20 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
             // dX += G(n) E_n : reads staging buffer `buf` (two 64-class halves) and the KB ring slices that held tile n
             auto gemm2 = [&](int first_stage, int buf, bool first) {
+                if (MODE != CE_STORE_G) {
+                    // A = G tile in tensor memory; B = the KB adjacent ring slices of this class tile read MN-major as ONE [128 k][64 KB n]
+                    // operand (the next 64-wide n block is one slice = TC_TILE_BYTES away; a tile never wraps the ring: NS = 3 KB)
+                    constexpr uint32_t idesc2t = umma_idesc(128, 64 * KB, 0, 1);
+                    const uint32_t b_addr = smem_u32(sE + first_stage * TC_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // 128 classes = 8 k-steps of 16 = 8 packed columns each
+                        umma_bf16_ts(tmem_dx, tmem_g + buf * 64 + k * 8, umma_desc(b_addr + k * 2048, TC_TILE_BYTES, 1024), idesc2t,
+                                     (first && k == 0) ? 0u : 1u);
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) umma_commit(&eempty[first_stage + kb]);
+                    umma_commit(&gempty[buf]);
+                    return;
+                }
                 const uint32_t a_addr = smem_u32(sOut0 + buf * 32768);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
@@ -156,14 +217,16 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 umma_commit(&gempty[buf]);
             };
             for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-                const int ntile = (w & 1) ? sh.num_n - sh.n_half : sh.n_half;
+                int blk_, nb_, ne_;
+                ce_item<MODE>(w, sh, blk_, nb_, ne_);
+                const int ntile = ne_ - nb_;
                 mbar_wait(xfull, xphase);
                 xphase ^= 1;
                 tc_fence_after();
                 int prev_stage = -1, prev_buf = 0;
                 bool first_g = true;
-                for (int tile = 0; tile < 2 * ntile; ++tile) {
-                    const bool sweep1 = tile >= ntile;
+                for (int tile = 0; tile < SWEEPS * ntile; ++tile) {
+                    const bool sweep1 = MODE == CE_ACCUM_T || tile >= ntile;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 128;
@@ -214,11 +277,14 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
         const int r = sub * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
-        const float ic = *inv_count;
+        const float ic = MODE == CE_ACCUM_T ? 0.f : *inv_count;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
-            const int blk = w >> 1, half = w & 1;
-            const int nb = half ? sh.n_half : 0, ne = half ? sh.num_n : sh.n_half;
+            int blk, nb, ne;
+            ce_item<MODE>(w, sh, blk, nb, ne);
+            const int half = w & 1;
             const int row = blk * 128 + r;
+            float gshift = 0.f, g_sum = 0.f;   // exponent shift of this row ; sum of this thread's G' entries (this half, this quarter)
+            if (MODE != CE_ACCUM_T) {
             const int t = row < sh.T ? (int)targets[row] : 0;
             const float icr = t != 0 ? ic : 0.f;   // ignore_index = 0 (and rows past the end)
             float m_run = -INFINITY, tl = 0.f;
@@ -273,16 +339,18 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             ce_bar_sync();
             const float4 pp = __ldcg(sh.stats + (size_t)(w ^ 1) * 128 + r);
             const float mm = fmaxf(mh, pp.x);
-            const float gshift = mm * kLog2e - __log2f(icr);   // icr == 0 (ignored row) -> +inf -> every entry of G' is 2^-inf = 0
+            gshift = mm * kLog2e - __log2f(icr);               // icr == 0 (ignored row) -> +inf -> every entry of G' is 2^-inf = 0
             if (half == 0 && cq == 0 && row < sh.T) row_stats[row] = make_float2(mm, tlh + pp.z);
-            float g_sum = 0.f;                                 // sum of this thread's G' entries (this half, this quarter)
+            }
             // ------------------------------------------------------------------ sweep 1: gradient tiles
-            if (warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
-            ce_bar_sync();                                     // (also: everybody has read s_part)
+            if (MODE == CE_STORE_G && warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
+            if (MODE != CE_ACCUM_T) ce_bar_sync();             // (also: everybody has read s_part)
             for (int n = nb; n < ne; ++n) {
+                if (MODE == CE_ACCUM_T && n + 1 < ne)   // next tile's shifts -> L1 while this tile is processed
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(col_shift + (n + 1) * 128 + cq * 32));
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-                if (FUSE_DX) mbar_wait(&gempty[gbuf], gphase ^ 1);   // the dX MMA that read this staging buffer two tiles ago is done
+                if (FUSE_DX) { mbar_wait(&gempty[gbuf], gphase ^ 1); tc_fence_after(); }   // the dX MMA that read this G buffer two tiles ago is done
                 unsigned char* sOut = sOut0 + gbuf * 32768;
                 {
                     float v[32];
@@ -291,19 +359,37 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained (it lives in registers now)
                     const int col0 = n * 128 + cq * 32;
+                    if (MODE == CE_ACCUM_T) {   // the shift belongs to the streaming (token) row = this tile's column
+                        const float4* cs = reinterpret_cast<const float4*>(col_shift + col0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // exp(s - max) * (1/count), folded into the exponent
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 s4 = __ldg(cs + j);
+                            v[4 * j] = ex2_fast(fmaf(v[4 * j], kLog2e, -s4.x));
+                            v[4 * j + 1] = ex2_fast(fmaf(v[4 * j + 1], kLog2e, -s4.y));
+                            v[4 * j + 2] = ex2_fast(fmaf(v[4 * j + 2], kLog2e, -s4.z));
+                            v[4 * j + 3] = ex2_fast(fmaf(v[4 * j + 3], kLog2e, -s4.w));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], kLog2e, -gshift));   // exp(s - max) * (1/count), folded into the exponent
+                    }
                     if (col0 + 32 > sh.C) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (col0 + i >= sh.C) v[i] = 0.f;
                     }
-                    {   // row sum of G' (four partial chains keep the adds off the critical path)
+                    if (MODE != CE_ACCUM_T) {   // row sum of G' (four partial chains keep the adds off the critical path)
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) { a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3]; }
                         g_sum += (a0 + a1) + (a2 + a3);
                     }
+                    if (MODE != CE_STORE_G) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                        tmem_st16(tmem_g + ((uint32_t)(sub * 32) << 16) + (uint32_t)(gbuf * 64 + cq * 16), pk);
+                    } else {
                     unsigned char* dst = sOut + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -312,8 +398,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
                         *reinterpret_cast<uint4*>(dst + ((((cq & 1) * 4 + j) ^ (r & 7)) << 4)) = u;
                     }
+                    }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (MODE != CE_STORE_G) {
+                    // each warp hands its 32 x 32 piece of the G tile to the MMA warp on its own: no CTA-wide barrier per class tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&gfull[gbuf]);
+                } else {
                 fence_proxy_async();   // generic-proxy smem writes -> visible to TMA and to tcgen05.mma (async proxy)
                 ce_bar_sync();
                 if (warp == 2 && lane == 0) {
@@ -324,15 +417,18 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     tma_store_commit();
                     tma_store_wait_read1();
                 }
-                ce_bar_sync();
+                ce_bar_sync();   // the staging buffer written two tiles ago has been read by its bulk store
+                }
                 if (gbuf == 1) gphase ^= 1;
                 gbuf ^= 1;
             }
             // row sums of this half -> global (four quarters combined through shared memory; slot 1 of s_part is free now)
-            s_part[(cq * 3 + 1) * 128 + r] = g_sum;
-            ce_bar_sync();
-            if (cq == 0 && row < sh.T)
-                row_sums[(size_t)half * sh.T + row] = (s_part[1 * 128 + r] + s_part[4 * 128 + r]) + (s_part[7 * 128 + r] + s_part[10 * 128 + r]);
+            if (MODE != CE_ACCUM_T) {
+                s_part[(cq * 3 + 1) * 128 + r] = g_sum;
+                ce_bar_sync();
+                if (cq == 0 && row < sh.T)
+                    row_sums[(size_t)half * sh.T + row] = (s_part[1 * 128 + r] + s_part[4 * 128 + r]) + (s_part[7 * 128 + r] + s_part[10 * 128 + r]);
+            }
             if (FUSE_DX && ne > nb) {
                 // ------------------------------------------------------------------ dX' partial of this half: TMEM -> += fp32 global
                 mbar_wait(dxfull, dxphase);
@@ -352,7 +448,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 if (lane == 0) mbar_arrive(dxempty);
             }
         }
-        if (warp == 2 && lane == 0) tma_store_wait_read();
+        if (MODE == CE_STORE_G && warp == 2 && lane == 0) tma_store_wait_read();
     }
     tc_fence_before();
     __syncthreads();
@@ -362,16 +458,31 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
     }
 }
 
-// X [T, D] bf16, E [C, D] bf16 -> G' [T, ldl] bf16 = exp(s - rowmax) * inv_count (columns >= C zeroed), row_sums [2][T], row_stats [T]
-// {max, target logit}, and (D <= 128) dx' [T, D] fp32 = G' E.  Returns through *fused_dx whether dx' was produced.  ce_finish_kernel
-// (rowwise.cuh) turns these into the loss, d loss / d x and the operand of the dE GEMM.
+// X [T, D] bf16, E [C, D] bf16 -> row_sums [2][T], row_stats [T] {max, target logit}, (D <= 128) dx' [T, D] fp32 = G' E with
+// G' = exp(s - rowmax) * inv_count, and - store_g - G' [T, ldl] bf16 (columns >= C zeroed) for a dE GEMM.  Returns through *fused_dx
+// whether dx' was produced.  ce_finish_kernel (rowwise.cuh) turns these into the loss, d loss / d x and the operands of the dE pass.
 inline size_t ce_scratch_bytes(int T) { return (size_t)2 * ((T + 127) / 128) * (128 * sizeof(float4) + sizeof(unsigned)) + 256; }
+template <int KB, int MODE>
+inline cudaError_t ce_set_attr() {
+    static bool attr_set_dev[64] = {false};
+    int attr_dev = 0;
+    cudaGetDevice(&attr_dev);
+    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_ce_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ce_smem_bytes<KB>());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return cudaSuccess;
+}
 // scratch: ce_scratch_bytes(T) bytes of device memory (partials + flags); dx must hold [T, D] fp32 and is zero-filled here
 template <int KB>
-inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, int C, int ldl, const long long* targets, const float* inv_count,
-                                float* row_sums, float2* row_stats, float* dx, bool* fused_dx, void* scratch, int num_sms, cudaStream_t st) {
+inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, bool store_g, int T, int C, int ldl, const long long* targets,
+                                const float* inv_count, float* row_sums, float2* row_stats, float* dx, bool* fused_dx, void* scratch,
+                                int num_sms, cudaStream_t st) {
     CUtensorMap tmX, tmE, tmG;
     const int D = 64 * KB;
+    if (KB > 2) store_g = true;
     bool ok = make_tmap_bf16(&tmX, X, T, D, D, 64, 128) && make_tmap_bf16(&tmE, E, C, D, D, 64, 128) && make_tmap(&tmG, G, false, T, ldl, ldl, 64, 128);
     if (!ok) return cudaErrorInvalidValue;
     CeShape sh;
@@ -379,6 +490,7 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
     sh.num_m = (T + 127) / 128;
     sh.num_n = (C + 127) / 128;
     sh.n_half = (sh.num_n + 1) / 2;
+    sh.nsplit = 2;
     sh.stats = reinterpret_cast<float4*>(scratch);
     sh.flags = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)2 * sh.num_m * 128 * sizeof(float4));
     cudaError_t me = cudaMemsetAsync(sh.flags, 0, (size_t)2 * sh.num_m * sizeof(unsigned), st);
@@ -388,19 +500,56 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int T, in
         me = cudaMemsetAsync(dx, 0, (size_t)T * D * sizeof(float), st);
         if (me != cudaSuccess) return me;
     }
-    auto kern = tc_ce_kernel<KB>;
-    static bool attr_set_dev[64] = {false};
-    int attr_dev = 0;
-    cudaGetDevice(&attr_dev);
-    bool& attr_set = attr_set_dev[attr_dev & 63];   // the attribute is per device
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ce_smem_bytes<KB>());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     // the two halves of a row block spin on each other: both must be resident at the same time -> even, persistent grid
     int grid = 2 * sh.num_m < num_sms ? 2 * sh.num_m : (num_sms & ~1);
-    launch_k(kern, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums, row_stats, dx);
+    if (store_g) {
+        me = ce_set_attr<KB, CE_STORE_G>();
+        if (me != cudaSuccess) return me;
+        launch_k(tc_ce_kernel<KB, CE_STORE_G>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums,
+                 row_stats, (const float*)nullptr, dx);
+    } else {
+        constexpr int M = KB <= 2 ? CE_KEEP_G : CE_STORE_G;
+        me = ce_set_attr<KB, M>();
+        if (me != cudaSuccess) return me;
+        launch_k(tc_ce_kernel<KB, M>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums, row_stats,
+                 (const float*)nullptr, dx);
+    }
+    return cudaGetLastError();
+}
+
+// dE [C, D] fp32 += G^T X without G in HBM (CE_ACCUM_T): G[t, c] = 2^(s_tc log2e - col_shift[t]) with s = X E^T recomputed, col_shift
+// [ceil(T/128)*128] = log2e * logsumexp_t - log2(inv_count_t) from ce_finish_kernel (+inf for ignored tokens and the padding).
+// One work item = a block of 128 classes x 1/nsplit of the token tiles; its accumulator leaves through 16-byte vector reductions.
+inline int ce_accum_nsplit(int num_m, int num_n, int num_sms) {
+    int best = 1; long long best_cost = -1;
+    for (int ns = 1; ns <= 16 && ns <= num_n; ++ns) {
+        const long long rounds = ((long long)num_m * ns + num_sms - 1) / num_sms;
+        const long long cost = rounds * ((num_n + ns - 1) / ns + 2);   // +2: resident load and accumulator flush of every item
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
+    }
+    return best;
+}
+template <int KB>
+inline cudaError_t launch_tc_ce_accum_t(const bf16* X, const bf16* E, const float* col_shift, float* dE, int T, int C, int num_sms,
+                                        cudaStream_t st) {
+    static_assert(KB <= 2, "second MMA needs D <= 128");
+    CUtensorMap tmRes, tmStream;
+    const int D = 64 * KB;
+    bool ok = make_tmap_bf16(&tmRes, E, C, D, D, 64, 128) && make_tmap_bf16(&tmStream, X, T, D, D, 64, 128);
+    if (!ok) return cudaErrorInvalidValue;
+    CeShape sh;
+    sh.T = C; sh.C = T; sh.ldl = 0;            // resident rows = classes, streaming rows = tokens
+    sh.num_m = (C + 127) / 128;
+    sh.num_n = (T + 127) / 128;
+    sh.n_half = 0;
+    sh.nsplit = ce_accum_nsplit(sh.num_m, sh.num_n, num_sms);
+    sh.stats = nullptr; sh.flags = nullptr;
+    cudaError_t me = ce_set_attr<KB, CE_ACCUM_T>();
+    if (me != cudaSuccess) return me;
+    const int items = sh.num_m * sh.nsplit;
+    const int grid = items < num_sms ? items : num_sms;
+    launch_k(tc_ce_kernel<KB, CE_ACCUM_T>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmRes, tmStream, tmStream, sh, (const long long*)nullptr,
+             (const float*)nullptr, (float*)nullptr, (float2*)nullptr, col_shift, dE);
     return cudaGetLastError();
 }
 
