@@ -28,6 +28,11 @@ class HstuLayerParams(C.Structure):
                                          "ffn1_b", "ffn2_w", "ffn2_b", "ln2_g", "ln2_b")]
 
 
+class HstuLayerParamsF32(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("proj_w_split", "proj_b", "pos_table", "time_table", "ln1_g", "ln1_b", "ffn1_w_split",
+                                         "ffn1_b", "ffn2_w_split", "ffn2_b", "ln2_g", "ln2_b")]
+
+
 class HstuLayerGrads(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("proj_w", "proj_b", "pos_table", "time_table", "ln1_g", "ln1_b", "ffn1_w",
                                          "ffn1_b", "ffn2_w", "ffn2_b", "ln2_g", "ln2_b")]
@@ -95,6 +100,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "grb_split3_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "grb_linear_f32x3_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "grb_linear_f32x3_bias_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "grb_hstu_layer_f32_workspace_bytes": (c_size_t, [P(HstuDims)]),
+    "grb_hstu_layer_forward_f32": (c_int, [P(HstuDims), P(HstuLayerParamsF32), P(HstuSeq), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "grb_layernorm_f32_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p]),
     "grb_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "grb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float,
                               c_float, c_float, c_float, c_float, c_int, c_void_p]),

@@ -14,6 +14,7 @@
 #include "attn_tc.cuh"
 #include "common.cuh"
 #include "dp_adam.cuh"
+#include "exact_f32.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 #include "rq_argmin.cuh"
@@ -1124,21 +1125,106 @@ int grb_split3_f32_to_bf16(const float* in, void* out_bf16, size_t rows, int K, 
     GRB_CUDA(cudaGetLastError());
     return 0;
 }
-int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16, int T, int N, int K, int act, float* y, void* stream) {
-    GRB_REQUIRE(x_split_bf16 && w_split_bf16 && y, "null argument");
-    GRB_REQUIRE(T > 0 && N % 4 == 0 && K % 8 == 0 && (act == 0 || act == 1), "bad shape T=%d N=%d K=%d act=%d", T, N, K, act);
-    GRB_REQUIRE(aligned16(x_split_bf16) && aligned16(w_split_bf16) && aligned16(y), "buffers must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int linear_f32x3(const bf16* xs, const bf16* ws, const float* bias, const float* res2, int T, int N, int K, int act, float* y, int ldy,
+                        cudaStream_t st) {
     const int K6 = 6 * K;
     // Two accumulators.  The tensor core adds each K = 16 group into the fp32 accumulator with truncation, an error relative to
     // the running sum per step: 288 steps over the six-term K (K = 768) measured 2e-5.  The five small cross terms (<= 2^-8 of
     // the result) are therefore summed on their own (their truncation is 2^-8 smaller), and the hi*hi term, K/16 steps, is
-    // added to that sum in the epilogue of a second pass together with the activation.  y doubles as the scratch of pass 1.
-    const bf16* xs = (const bf16*)x_split_bf16;
-    const bf16* ws = (const bf16*)w_split_bf16;
-    GRB_CUDA((launch_tc_gemm<0, 0>(xs + K, ws + K, T, N, 5 * K, K6, K6, 1, TcEpiF32{nullptr, N, 1.f}, y, nullptr, N, sm_count(), st)));
-    if (act == 1) GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<1>{y, N}, y, nullptr, N, sm_count(), st)));
-    else GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<0>{y, N}, y, nullptr, N, sm_count(), st)));
+    // added to that sum in the epilogue of a second pass together with bias, activation and residual.  y doubles as the scratch of pass 1.
+    GRB_CUDA((launch_tc_gemm<0, 0>(xs + K, ws + K, T, N, 5 * K, K6, K6, 1, TcEpiF32{nullptr, ldy, 1.f}, y, nullptr, ldy, sm_count(), st)));
+    if (act == 1) GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<1>{y, ldy, bias, res2}, y, nullptr, ldy, sm_count(), st)));
+    else GRB_CUDA((launch_tc_gemm<0, 0>(xs, ws, T, N, K, K6, K6, 1, TcEpiActResF32<0>{y, ldy, bias, res2}, y, nullptr, ldy, sm_count(), st)));
+    return 0;
+}
+int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16, int T, int N, int K, int act, float* y, void* stream) {
+    GRB_REQUIRE(x_split_bf16 && w_split_bf16 && y, "null argument");
+    GRB_REQUIRE(T > 0 && N % 4 == 0 && K % 8 == 0 && (act == 0 || act == 1), "bad shape T=%d N=%d K=%d act=%d", T, N, K, act);
+    GRB_REQUIRE(aligned16(x_split_bf16) && aligned16(w_split_bf16) && aligned16(y), "buffers must be 16-byte aligned");
+    return linear_f32x3((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, nullptr, nullptr, T, N, K, act, y, N, static_cast<cudaStream_t>(stream));
+}
+int grb_linear_f32x3_bias_forward(const void* x_split_bf16, const void* w_split_bf16, const float* bias, const float* residual, int T, int N,
+                                  int K, int act, float* y, int ldy, void* stream) {
+    GRB_REQUIRE(x_split_bf16 && w_split_bf16 && y, "null argument");
+    GRB_REQUIRE(T > 0 && N > 0 && ldy >= N && ldy % 4 == 0 && K % 8 == 0 && (act == 0 || act == 1), "bad shape T=%d N=%d K=%d ldy=%d act=%d", T, N, K, ldy, act);
+    GRB_REQUIRE(aligned16(x_split_bf16) && aligned16(w_split_bf16) && aligned16(y) && (!residual || aligned16(residual)), "buffers must be 16-byte aligned");
+    return linear_f32x3((const bf16*)x_split_bf16, (const bf16*)w_split_bf16, bias, residual, T, N, K, act, y, ldy, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ fp32-exact HSTU block, forward
+struct LayerF32Work {
+    bf16* xs; float* P; float* O; float* x1; float* xn; float* h; bf16* hs; size_t bytes;
+};
+static LayerF32Work carve_f32(void* base, size_t T, size_t D) {
+    LayerF32Work w;
+    size_t off = 0;
+    auto take = [&](size_t n) { void* p = base ? (char*)base + off : nullptr; off += (n + 255) & ~size_t(255); return p; };
+    w.xs = (bf16*)take(T * 6 * D * 2);
+    w.P = (float*)take(T * 4 * D * 4);
+    w.O = (float*)take(T * D * 4);
+    w.x1 = (float*)take(T * D * 4);
+    w.xn = (float*)take(T * D * 4);
+    w.h = (float*)take(T * 4 * D * 4);
+    w.hs = (bf16*)take(T * 24 * D * 2);
+    w.bytes = off;
+    return w;
+}
+size_t grb_hstu_layer_f32_workspace_bytes(const grb_hstu_dims* d) {
+    if (!d || d->B <= 0 || d->L <= 0 || d->D <= 0) return 0;
+    return carve_f32(nullptr, (size_t)d->B * d->L, d->D).bytes;
+}
+int grb_hstu_layer_forward_f32(const grb_hstu_dims* d, const grb_hstu_layer_params_f32* p, const grb_hstu_seq* s, const float* x, float* y,
+                               void* workspace, void* stream) {
+    GRB_TRY(check_dims(d));
+    GRB_REQUIRE(p && s && x && y && workspace, "null argument");
+    GRB_REQUIRE(p->proj_w_split && p->proj_b && p->pos_table && p->ln1_g && p->ln1_b && p->ffn1_w_split && p->ffn1_b && p->ffn2_w_split &&
+                    p->ffn2_b && p->ln2_g && p->ln2_b, "null parameter pointer");
+    GRB_REQUIRE(s->bias_index && s->ld_index >= d->L && s->ld_index % 8 == 0, "the fp32 path reads the [B, L, ld] bias index matrix");
+    GRB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(workspace), "buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = d->B * d->L, D = d->D, DH = D / d->H;
+    LayerF32Work w = carve_f32(workspace, T, D);
+    GRB_TRY(join_pending(st));
+    // P = silu(x Wp^T + bp)                                                                   (hstu.py:234-235)
+    GRB_TRY(grb_split3_f32_to_bf16(x, w.xs, T, D, 0, stream));
+    GRB_TRY(linear_f32x3(w.xs, (const bf16*)p->proj_w_split, p->proj_b, nullptr, T, 4 * D, D, 1, w.P, 4 * D, st));
+    // O = silu(Q K^T + bias) V                                                                (hstu.py:244-267)
+    {
+        HstuAttnF32Args a{w.P, 4 * D, d->B, d->L, d->H, {}, w.O};
+        // same conventions as make_attn_args(): uniform position buckets collapse to one effective bucket
+        a.bias.wpos = p->pos_table + (s->pos_uniform ? (size_t)s->pos_bucket0 * d->H : 0);
+        const bool has_time = p->time_table != nullptr && s->has_time && d->ntime > 0;
+        a.bias.wtime = has_time ? p->time_table : nullptr;
+        a.bias.bias_index = s->bias_index; a.bias.ldix = s->ld_index;
+        a.bias.npos = s->pos_uniform ? 1 : d->npos; a.bias.ntime = has_time ? d->ntime : 0;
+        a.bias.pos_uniform = s->pos_uniform; a.bias.pos_bucket0 = 0;
+        int rc = DH == 32 ? launch_hstu_attn_f32<32>(a, st) : launch_hstu_attn_f32<64>(a, st);
+        GRB_REQUIRE(rc == 0, "fp32 attention launch failed");
+    }
+    // x1 = x + LN1(O) * U ; xn = LN2(x1)                                                      (hstu.py:271-278)
+    {
+        LnGateF32Args a{w.O, w.P, 4 * D, x, p->ln1_g, p->ln1_b, p->ln2_g, p->ln2_b, w.x1, w.xn, T, 1e-5f};
+        const int grid = row_grid(T);
+        if (D == 64) launch_k(ln_gate_f32_kernel<2>, grid, 256, 0, st, a);
+        else if (D == 128) launch_k(ln_gate_f32_kernel<4>, grid, 256, 0, st, a);
+        else launch_k(ln_gate_f32_kernel<8>, grid, 256, 0, st, a);
+        GRB_CUDA(cudaGetLastError());
+    }
+    // y = x1 + (silu(xn W1^T + b1) W2^T + b2)                                                 (hstu.py:210-214, :278)
+    GRB_TRY(grb_split3_f32_to_bf16(w.xn, w.xs, T, D, 0, stream));
+    GRB_TRY(linear_f32x3(w.xs, (const bf16*)p->ffn1_w_split, p->ffn1_b, nullptr, T, 4 * D, D, 1, w.h, 4 * D, st));
+    GRB_TRY(grb_split3_f32_to_bf16(w.h, w.hs, T, 4 * D, 0, stream));
+    GRB_TRY(linear_f32x3(w.hs, (const bf16*)p->ffn2_w_split, p->ffn2_b, w.x1, T, D, 4 * D, 0, y, D, st));
+    return 0;
+}
+int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, float eps, int T, int D, float* y, void* stream) {
+    GRB_REQUIRE(x && g && b && y && T > 0 && (D == 64 || D == 128 || D == 256), "bad argument T=%d D=%d", T, D);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = row_grid(T);
+    if (D == 64) launch_k(ln_f32_kernel<2>, grid, 256, 0, st, x, g, b, y, T, eps);
+    else if (D == 128) launch_k(ln_f32_kernel<4>, grid, 256, 0, st, x, g, b, y, T, eps);
+    else launch_k(ln_f32_kernel<8>, grid, 256, 0, st, x, g, b, y, T, eps);
+    GRB_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -556,7 +556,8 @@ struct TcEpiActF32 {
         }
     }
 };
-// out = ACT(res + acc) -> fp32 : second pass of the split-bf16 GEMM (res = the sum of the five small cross terms)
+// out = ACT(res + acc + bias) + res2 -> fp32 : second pass of the split-bf16 GEMM (res = the sum of the five small cross terms;
+// bias [N] and res2 [M, ld] nullable: the linear layers and the residual connection of the fp32-exact HSTU block)
 template <int ACT>
 struct TcEpiActResF32 {
     static constexpr int kOut = 3;
@@ -564,13 +565,20 @@ struct TcEpiActResF32 {
     static constexpr bool kAux = false;
     const float* res;
     int ld;
+    const float* bias;
+    const float* res2;
     GRB_DEVINL void prepare() {}
     GRB_DEVINL void preload(int row, int col0, int nvalid, float (&y)[32]) const { load_f32x32(res + (size_t)row * ld + col0, y, nvalid); }
-    GRB_DEVINL void operator()(int, int, float (&v)[32], float (&)[32], int, const float (&y)[32]) const {
+    GRB_DEVINL void operator()(int row, int col0, float (&v)[32], float (&)[32], int nvalid, const float (&y)[32]) const {
+        float bb[32], rr[32];
+        if (bias) load_f32x32(bias + col0, bb, nvalid);
+        if (res2) load_f32x32(res2 + (size_t)row * ld + col0, rr, nvalid);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const float z = v[i] + y[i];
-            v[i] = ACT == 1 ? __fdiv_rn(z, 1.f + exp_accurate(-z)) : z;
+            float z = v[i] + y[i];
+            if (bias) z += bb[i];
+            z = ACT == 1 ? __fdiv_rn(z, 1.f + exp_accurate(-z)) : z;
+            v[i] = res2 ? z + rr[i] : z;
         }
     }
 };

@@ -560,6 +560,56 @@ def linear_f32x3(x_split: torch.Tensor, w_split: torch.Tensor, act: int = 0) -> 
     return y
 
 
+def linear_f32x3_bias(x_split: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None,
+                      act: int = 0) -> torch.Tensor:
+    """y = act(x W^T + bias) + residual in fp32 accuracy; N need not be a multiple of 4 (the output pitch is padded and sliced)."""
+    K6 = x_split.shape[-1]
+    T, N = x_split.numel() // K6, w_split.shape[0]
+    ldy = (N + 3) // 4 * 4
+    if residual is not None and ldy != N:
+        raise _lib.GrbError("genrec_b200 error -1: residual needs N % 4 == 0")
+    y = torch.empty(*x_split.shape[:-1], ldy, dtype=torch.float32, device=x_split.device)
+    with torch.cuda.device(x_split.device):
+        check(_lib.load().grb_linear_f32x3_bias_forward(ptr(x_split), ptr(w_split), ptr(bias), ptr(residual), T, N, K6 // 6, act, ptr(y), ldy,
+                                                        stream_ptr(x_split.device)))
+    return y[..., :N] if ldy != N else y
+
+
+def layernorm_f32(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    require_cuda(x)
+    require_f32(x, g, b)
+    x = x.detach().contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().grb_layernorm_f32_forward(ptr(x), ptr(g.detach()), ptr(b.detach()), float(eps), x.numel() // x.shape[-1], x.shape[-1],
+                                                    ptr(y), stream_ptr(x.device)))
+    return y
+
+
+def hstu_layer_forward_f32(x: torch.Tensor, meta: SeqMeta, H: int, npos: int, ntime: int, split_w: dict, params) -> torch.Tensor:
+    """fp32-exact forward of one HSTU block (csrc/exact_f32.cuh; hstu.py:222-280 without autocast).  ``split_w`` = the three weight
+    matrices pre-split by split3(w, 1); ``params`` in PARAM_ORDER.  Forward only."""
+    require_cuda(x)
+    require_f32(x)
+    lib = _lib.load()
+    B, L, D = x.shape
+    xc = x.detach().contiguous()
+    (_, proj_b, pos_t, time_t, ln1_g, ln1_b, _, ffn1_b, _, ffn2_b, ln2_g, ln2_b) = params
+    meta._build_bias_index()
+    join_deferred(x.device)
+    seq = HstuSeq(ptr(meta.bias_index), meta.ld, 1 if meta.timestamps is not None else 0, 1 if meta.pos_uniform else 0, meta.pos_bucket0,
+                  ptr(meta.timestamps), ptr(meta.pad), None, None, ptr(meta.time_thr))
+    d = _dims(B, L, D, H, npos, ntime, 0.0, 0, None, 0)
+    p = _lib.HstuLayerParamsF32(ptr(split_w["proj_w"]), ptr(proj_b.detach()), ptr(pos_t.detach()), ptr(time_t.detach()) if time_t is not None else None,
+                                ptr(ln1_g.detach()), ptr(ln1_b.detach()), ptr(split_w["ffn1_w"]), ptr(ffn1_b.detach()), ptr(split_w["ffn2_w"]),
+                                ptr(ffn2_b.detach()), ptr(ln2_g.detach()), ptr(ln2_b.detach()))
+    ws = _u8(lib.grb_hstu_layer_f32_workspace_bytes(C.byref(d)), x.device)
+    y = torch.empty_like(xc)
+    with torch.cuda.device(x.device):
+        check(lib.grb_hstu_layer_forward_f32(C.byref(d), C.byref(p), C.byref(seq), ptr(xc), ptr(y), ptr(ws), stream_ptr(x.device)))
+    return y
+
+
 def adam_step(p, g, m, v, p_bf16, state, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, zero_grad=True):
     with torch.cuda.device(p.device):
         check(_lib.load().grb_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), ptr(state), lr, beta1, beta2, eps, weight_decay,

@@ -160,6 +160,28 @@ class HSTULayer(nn.Module):
         self._bf16 = {}            # name -> (version, tensor) : eval-mode cache of bf16 weight mirrors
         self._bf16_provider = None  # set by genrec_b200.optim.FlatAdam: param -> always-fresh bf16 view
         self._grad_sink = None      # set by FlatAdam: param -> view of the flat gradient buffer (kernels accumulate there)
+        self.precision = "bf16"     # "fp32": the fp32-exact forward path (HSTU.set_precision)
+        self._split = {}            # name -> (version, tensor): three-term bf16 splits of the weight matrices (fp32 path)
+
+    def _split_weight(self, name: str, param: torch.Tensor) -> torch.Tensor:
+        ent = self._split.get(name)
+        if ent is None or ent[0] != param._version or ent[1].device != param.device:
+            ent = (param._version, Fn.split3(param, 1))
+            self._split[name] = ent
+        return ent[1]
+
+    def _run_f32(self, x: torch.Tensor, meta: Fn.SeqMeta) -> torch.Tensor:
+        """fp32-exact forward (what the reference computes without autocast; 1e-5 parity target).  Forward only."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("genrec_b200: precision='fp32' is a forward-only path (evaluation / inference / parity); "
+                               "wrap the call in torch.no_grad() or train with precision='bf16'")
+        if self.training and self.dropout.p > 0:
+            raise RuntimeError("genrec_b200: precision='fp32' has no dropout; call model.eval()")
+        sw = {"proj_w": self._split_weight("proj_w", self.projection.weight),
+              "ffn1_w": self._split_weight("ffn1_w", self.ffn[0].weight),
+              "ffn2_w": self._split_weight("ffn2_w", self.ffn[3].weight)}
+        return Fn.hstu_layer_forward_f32(x, meta, self.num_heads, self.position_bias.num_buckets,
+                                         self.temporal_bias.num_buckets if self.use_temporal_bias else 0, sw, self._params())
 
     # -- bf16 operand mirrors of the three weight matrices
     def _mirror(self, name: str, param: torch.Tensor) -> torch.Tensor:
@@ -181,6 +203,8 @@ class HSTULayer(nn.Module):
                 self.ffn[3].bias, self.ffn_norm.weight, self.ffn_norm.bias)
 
     def _run(self, x: torch.Tensor, meta: Fn.SeqMeta, seed: int, seed_dev) -> torch.Tensor:
+        if self.precision == "fp32":
+            return self._run_f32(x, meta)
         bf16w = {"proj_w": self._mirror("proj_w", self.projection.weight),
                  "ffn1_w": self._mirror("ffn1_w", self.ffn[0].weight),
                  "ffn2_w": self._mirror("ffn2_w", self.ffn[3].weight)}
@@ -227,6 +251,8 @@ class HSTU(nn.Module):
         self.final_norm = nn.LayerNorm(embed_dim)
         self.return_train_logits = False
         self._table_bf16 = None
+        self._table_split = None
+        self.precision = "bf16"
         self._bf16_provider = None
         self._grad_sink = None
         self._unit_loss_grad = False   # FlatAdam(unit_loss_grad=True): head gradients go straight into the flat buffer (see HeadLossFn)
@@ -248,6 +274,26 @@ class HSTU(nn.Module):
             elif isinstance(module, nn.LayerNorm):
                 nn.init.ones_(module.weight)
                 nn.init.zeros_(module.bias)
+
+    def set_precision(self, precision: str) -> "HSTU":
+        """"bf16" (default): bf16 tensor-core operands, fp32 accumulation and residual stream - the reference under
+        Accelerator(mixed_precision="bf16").  "fp32": the fp32-exact forward path (split-bf16 GEMMs + fp32 attention / LayerNorm,
+        csrc/exact_f32.cuh) - the reference without autocast, to 1e-5; evaluation / inference only."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        for layer in self.layers:
+            layer.precision = precision
+        return self
+
+    def _head_logits_f32(self, x: torch.Tensor) -> torch.Tensor:
+        w = self.item_embedding.weight
+        ent = self._table_split
+        if ent is None or ent[0] != w._version or ent[1].device != w.device:
+            ent = (w._version, Fn.split3(w, 1))
+            self._table_split = ent
+        xf = Fn.layernorm_f32(x, self.final_norm.weight, self.final_norm.bias, self.final_norm.eps)
+        return Fn.linear_f32x3_bias(Fn.split3(xf, 0), ent[1], None, None, 0)
 
     def _table_mirror(self) -> torch.Tensor:
         w = self.item_embedding.weight
@@ -300,6 +346,10 @@ class HSTU(nn.Module):
                 targets: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """hstu.py:99-148.  Returns (logits [B,L,V+1] fp32 | None, loss | None)."""
         x = self.encode(input_ids, timestamps)
+        if self.precision == "fp32":
+            if targets is not None:
+                raise RuntimeError("genrec_b200: precision='fp32' computes logits only (no loss / training)")
+            return self._head_logits_f32(x), None
         table = self.item_embedding.weight
         table_bf16 = self._table_mirror()
         loss = None
@@ -319,6 +369,8 @@ class HSTU(nn.Module):
         """[B, V+1] fp32 logits of the LAST position only (all that predict() / evaluation read): the tied-embedding GEMM runs
         on B rows instead of B*L."""
         x = self.encode(input_ids, timestamps)
+        if self.precision == "fp32":
+            return self._head_logits_f32(x[:, -1:, :].contiguous())[:, 0, :]
         return Fn.head_logits(x[:, -1:, :].contiguous(), self.final_norm.weight, self.final_norm.bias, self.item_embedding.weight,
                               self._table_mirror(), self.final_norm.eps)[:, 0, :]
 

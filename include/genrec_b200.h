@@ -209,6 +209,30 @@ int grb_layernorm_backward(const float* dy, const float* x, const float* stats, 
  *   grb_linear_f32x3_forward: y [T, N] fp32 = act(x [T, K] @ W [N, K]^T), both operands pre-split ; act 0 none, 1 silu */
 int grb_split3_f32_to_bf16(const float* in, void* out_bf16, size_t rows, int K, int operand, void* stream);
 int grb_linear_f32x3_forward(const void* x_split_bf16, const void* w_split_bf16, int T, int N, int K, int act, float* y, void* stream);
+/*   grb_linear_f32x3_bias_forward: y [T, ldy] fp32 = act(x @ W^T + bias) + residual ; bias [N] and residual [T, ldy] may be NULL,
+ *   ldy >= N a multiple of 4 (the tied head has N = V + 1) */
+int grb_linear_f32x3_bias_forward(const void* x_split_bf16, const void* w_split_bf16, const float* bias, const float* residual, int T,
+                                  int N, int K, int act, float* y, int ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fp32-exact HSTU block (forward)
+ * What the reference computes WITHOUT autocast (plain fp32 modules, hstu.py:222-280), for the "1e-5 (fp32)" parity target:
+ * every linear layer is the split-bf16 GEMM above, attention / LayerNorm / gating are fp32 CUDA-core kernels
+ * (csrc/exact_f32.cuh).  Forward only - evaluation, inference and parity; dropout is the identity.  The weight matrices arrive
+ * pre-split (grb_split3_f32_to_bf16, operand 1): proj [4D, 6D], ffn1 [4D, 6D], ffn2 [D, 24D].  `s` must carry the
+ * [B, L, ld_index] bias index matrix of grb_hstu_bias_index(). */
+typedef struct {
+    const void* proj_w_split; const float* proj_b;
+    const float* pos_table; const float* time_table;   /* [npos, H], [ntime, H] or NULL */
+    const float* ln1_g; const float* ln1_b;
+    const void* ffn1_w_split; const float* ffn1_b;
+    const void* ffn2_w_split; const float* ffn2_b;
+    const float* ln2_g; const float* ln2_b;
+} grb_hstu_layer_params_f32;
+size_t grb_hstu_layer_f32_workspace_bytes(const grb_hstu_dims* d);
+int grb_hstu_layer_forward_f32(const grb_hstu_dims* d, const grb_hstu_layer_params_f32* p, const grb_hstu_seq* s, const float* x, float* y,
+                               void* workspace, void* stream);
+/* y [T, D] fp32 = LayerNorm(x) in fp32 (the final norm in front of the fp32 head, hstu.py:134) */
+int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, float eps, int T, int D, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ optimizer / casts */
 int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);

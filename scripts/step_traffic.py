@@ -25,7 +25,7 @@ for r in rows[hdr + 1:]:
 seq = list(launches.values())
 starts = [i for i, d in enumerate(seq) if d["name"].startswith("embed_fwd")]
 seq = seq[starts[-2]:starts[-1]] if len(starts) >= 2 else seq[starts[-1]:]
-HEAD = ("tc_ce", "ce_count", "embed_", "adam", "ln_fwd", "ln_bwd", "at::", "hstu_bias_index", "cast_flat")
+HEAD = ("tc_ce", "ce_count", "ce_finish", "embed_", "adam", "ln_fwd", "ln_bwd", "at::", "hstu_bias_index", "hstu_seq_prep", "assert_unit", "cast_flat")
 agg = collections.OrderedDict()
 tot = [0.0, 0.0, 0.0]
 blk = [0.0, 0.0, 0.0]

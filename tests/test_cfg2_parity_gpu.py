@@ -268,16 +268,21 @@ def test_deferred_weight_gradients_equal_inline_ones():
             m = HSTU(300, 70, 64, 2, 2, dropout=0.0).to(dev).train()
             opt = FlatAdam(m, lr=1e-3, unit_loss_grad=True, defer_weight_grads=defer)
             Fn.set_defer_weight_grads(defer)
+            gs = []
             for _ in range(2):
                 _, loss = m(ids, ts, tg)
                 loss.backward()
                 opt.sync_grads()
-                g = opt.grad.clone()
+                gs.append(opt.grad.clone())
                 opt.step()
             torch.cuda.synchronize()
-            res.append((g, opt.flat.clone()))
+            res.append((gs, opt.flat.clone()))
     finally:
         Fn.set_defer_weight_grads(False)
         Fn.join_deferred(dev)
-    torch.testing.assert_close(res[1][0], res[0][0], rtol=1e-3, atol=1e-5 * res[0][0].abs().max().item())
+    # first step: same kernels, same inputs - only the order of the fp32 reductions (red.global.add) differs between the schedules
+    torch.testing.assert_close(res[1][0][0], res[0][0][0], rtol=1e-3, atol=1e-5 * res[0][0][0].abs().max().item())
+    # second step: an ulp of difference in a first-step gradient can flip the bf16 rounding of one updated weight in the operand
+    # mirror (seen in 3 of 40 repetitions, scripts/flake_deferred.py: 10 elements, 5e-5 of the largest gradient)
+    torch.testing.assert_close(res[1][0][1], res[0][0][1], rtol=1e-3, atol=3e-4 * res[0][0][1].abs().max().item())
     assert ((res[1][1] - res[0][1]).abs() > 1e-4).float().mean().item() < 1e-3
