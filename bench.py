@@ -215,7 +215,7 @@ def run_cuda_eager(args, rank, world, local_rank):
     line = dict(impl="cuda_eager", metric=METRIC, value=r["seq_per_s"], unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 autocast", data="synthetic",
                 config=dict(workload=workload_name(L) + " - reference algorithm, PyTorch eager on cuda:0", batch_per_step=args.eager_batch))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(L):
@@ -239,7 +239,7 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=r["seq_per_s"], unit=UNIT, cores=r["threads"], kind="port",
                                   sample=f"{len(r['times'])} steps of B={args.cpu_batch} x L={L}"),
                 e2e=dict(value=r["seq_per_s"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -401,12 +401,13 @@ def run_ours(args, rank, world, local_rank):
                 e2e=dict(value=gb * K / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / K, wall_ms_per_step=wall_e2e / K, ms_per_step_pct=pct_e2e),
                 gpu_launches=launches_per_step * K, clocks=clocks, roofline=roof, cpu_baseline=cpu, cuda_eager_baseline=eager)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the block stack's kernels for one fwd+bwd, from the committed ncu
 # capture of the same command (profiles/*_step_dram_traffic.txt, scripts/step_traffic.py); keyed by (B, L, D, layers)
-TRAFFIC_NCU = {(128, 200, 128, 4): 2.106e9}
+TRAFFIC_NCU = {(128, 200, 128, 4): 2.023e9,      # profiles/r2_step_cfg2_dram_traffic.txt
+               (32, 2048, 256, 8): 38.780e9}     # profiles/r2_step_cfg3_dram_traffic.txt
 
 
 def block_roofline(model, B, L, dev, K):
@@ -462,7 +463,7 @@ def block_roofline(model, B, L, dev, K):
     flops = (72 * L * D * D + 6 * D * L * (L + 1)) * B * nl
     ach = flops / (ms * 1e-3) / 1e12
     # DRAM bytes (read + write) of the block stack's kernels for one fwd+bwd at the default geometry, summed from the ncu
-    # capture profiles/r1_step_dram_traffic.txt (scripts/step_traffic.py); not re-measured here (needs a profiler)
+    # captures profiles/r2_step_cfg{2,3}_dram_traffic.txt (scripts/step_traffic.py); not re-measured here (needs a profiler)
     traffic = TRAFFIC_NCU.get((B, L, D, nl))
     return dict(bound="tensor", kernel="hstu_block_stack_fwd_bwd", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                 peak_source=which, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
@@ -470,8 +471,30 @@ def block_roofline(model, B, L, dev, K):
                 unit_of_work=f"{nl} layers x B={B} sequences x L={L}")
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at world > 1), so file descriptor 1
+    is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

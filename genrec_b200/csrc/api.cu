@@ -12,6 +12,7 @@
 #include "attn_hstu.cuh"
 #include "attn_sasrec.cuh"
 #include "attn_tc.cuh"
+#include "beam.cuh"
 #include "common.cuh"
 #include "dp_adam.cuh"
 #include "exact_f32.cuh"
@@ -1228,6 +1229,35 @@ int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, fl
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ TIGER constrained beam step
+int grb_trie_log_softmax(const float* logits, int rows, int V, const int32_t* node, const int32_t* child_off, const int32_t* child_tok,
+                         int n_nodes, int use_trie, int vocab_offset, int num_embeddings, float temperature, float* probs, float* logp,
+                         void* stream) {
+    GRB_REQUIRE(logits && probs && logp && rows >= 0 && V > 0 && V <= 1 << 20, "bad argument rows=%d V=%d", rows, V);
+    GRB_REQUIRE(!use_trie || (node && child_off && n_nodes > 0), "trie arrays missing");
+    GRB_REQUIRE(temperature > 0.f, "temperature must be positive");
+    if (rows == 0) return 0;
+    TrieCsr t{child_off, child_tok, nullptr, n_nodes};
+    const size_t smem = (size_t)((V + 31) / 32) * 4;
+    launch_k(trie_log_softmax_kernel, rows, 256, smem, static_cast<cudaStream_t>(stream), logits, V, node, t, use_trie, vocab_offset,
+             num_embeddings, temperature, probs, logp);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int grb_beam_select(const int64_t* beam_seqs, const float* beam_logps, const int64_t* cand_tok, const float* cand_logp, const int32_t* nodes,
+                    const int32_t* child_off, const int32_t* child_tok, const int32_t* child_node, int n_nodes, int B, int K, int KK, int S,
+                    int64_t* new_seqs, float* new_logps, int32_t* new_nodes, void* stream) {
+    GRB_REQUIRE(beam_logps && cand_tok && cand_logp && new_seqs && new_logps && (S == 0 || beam_seqs), "null argument");
+    GRB_REQUIRE(B >= 0 && K >= 1 && K <= 32 && KK >= 1 && K * KK <= BEAM_MAX_CAND && S >= 0, "bad shape B=%d K=%d KK=%d S=%d (K <= 32, K*KK <= 1024)", B, K, KK, S);
+    GRB_REQUIRE(!new_nodes || (nodes && child_off && child_tok && child_node && n_nodes > 0), "trie arrays missing");
+    if (B == 0) return 0;
+    BeamSelectArgs a{reinterpret_cast<const long long*>(beam_seqs), beam_logps, reinterpret_cast<const long long*>(cand_tok), cand_logp, nodes,
+                     TrieCsr{child_off, child_tok, child_node, n_nodes}, K, KK, S, reinterpret_cast<long long*>(new_seqs), new_logps, new_nodes};
+    launch_k(beam_select_kernel, B, BEAM_MAX_CAND, 0, static_cast<cudaStream_t>(stream), a);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ optimizer / casts
 int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream) {
     GRB_REQUIRE(in && out_bf16, "null argument");
@@ -1313,7 +1343,24 @@ int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GRB_REQUIRE(emb == nullptr || aligned16(emb), "emb must be 16-byte aligned");
     GRB_REQUIRE(res == nullptr || aligned16(res), "res must be 16-byte aligned");
-    const bool legacy = getenv("GRB_RQ") != nullptr && strcmp(getenv("GRB_RQ"), "thread") == 0;   // one-thread-per-row first generation
+    // Three kernels (rq_argmin.cuh).  Default: the register-blocked tile kernel (D = 32, K a multiple of 256, tile fits shared
+    // memory).  GRB_RQ = tile | split | thread forces one; split / thread are the earlier generations, kept as cross-checks
+    // (tests/test_rq_gpu.py compares all three) and for the shapes the tile kernel does not cover.
+    const char* rq_env = getenv("GRB_RQ");
+    const bool force_thread = rq_env != nullptr && strcmp(rq_env, "thread") == 0;
+    const bool force_split = rq_env != nullptr && strcmp(rq_env, "split") == 0;
+    {
+        const bool stage = emb != nullptr || res != nullptr;
+        const size_t smem = rq_tile_smem_bytes(D, K, levels, stage);
+        if (!force_thread && !force_split && D == 32 && K % 256 == 0 && smem <= 220 * 1024) {
+            GRB_TRY(set_smem(rq_residual_argmin_tile_kernel<32>, smem));
+            const unsigned grid = (unsigned)((N + RQT_ROWS - 1) / RQT_ROWS);
+            launch_k(rq_residual_argmin_tile_kernel<32>, grid, RQ_THREADS, smem, st, a);
+            GRB_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
+    const bool legacy = force_thread || (!force_split && N > (int64_t)sm_count() * RQ_THREADS * 4);
     if (!legacy && K % 8 == 0) {
         // four threads per row (see rq_argmin.cuh); two rows per thread once there is more than a wave of work (FMA : LDS = 8 : 1)
         const int rows = (D == 32 && N > (int64_t)sm_count() * RQ_ROWS_PER_CTA * 4) ? 2 : 1;

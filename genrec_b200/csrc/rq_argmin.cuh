@@ -311,4 +311,171 @@ __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_split_kernel(Rq
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ register-blocked tile variant
+// The two kernels above feed 4 (or 8) FFMA per 16-byte shared-memory load; an LDS.128 delivers 512 B to the register file and the
+// SM moves 128 B per clock, so they are bound by the shared-memory -> register path at ~25 % (50 %) of the FMA rate, and at the
+// catalogue size (N = 12,101) additionally by one serial chain of 3 x 256 (or 64) codes per thread on a third of the SMs.
+// This variant is the distance "GEMM" on the CUDA cores: a CTA owns 128 item rows; the residual tile and the level's codebook sit
+// TRANSPOSED in shared memory (rT[d][row], cT[d][code]); thread (rg, cg) accumulates an 8-row x 16-code block of dot products in
+// registers - per d: 2 + 4 LDS.128 feed 64 packed FFMA2 = 128 fma (the 3-register FFMA issues every second clock per SM
+// sub-partition: ~37 TFLOP/s; fma.rn.f32x2 does two per issue).  Every (row, code) dot product is still ONE fmaf chain over d = 0 .. D-1
+// and the distance is still (|r|^2 + |c|^2) - 2 r.c with strict '<' over ascending code indices, so ids are bit-identical to the
+// kernels above (tests/test_rq_gpu.py).  The 16 threads that share a row meet through 4 shuffle steps (lower index wins ties).
+// Outputs in the reference's [N, D, levels] layout are staged per tile and written as one contiguous span.
+constexpr int RQT_ROWS = 128;             // rows per CTA
+constexpr int RQT_RLD = RQT_ROWS + 4;     // row pitch of the transposed tiles (floats); +4 keeps 16-byte alignment of the float4 loads
+template <int D>
+__global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(RqArgs a) {
+    pdl_wait();
+    extern __shared__ __align__(16) float rq_smem[];
+    const int KLD = a.K + 4;
+    float* rT = rq_smem;                               // [D][RQT_RLD]   residual, transposed
+    float* cT = rT + D * RQT_RLD;                      // [D][KLD]       codebook level, transposed
+    float* cn = cT + D * KLD;                          // [K]            |c|^2
+    float* xn = cn + ((a.K + 3) & ~3);                 // [128]          |r|^2
+    float* lossv = xn + RQT_ROWS;                      // [128]
+    int* sid = reinterpret_cast<int*>(lossv + RQT_ROWS);          // [128][levels] chosen codes
+    float* st_emb = reinterpret_cast<float*>(sid + RQT_ROWS * a.levels + ((4 - (RQT_ROWS * a.levels) % 4) % 4));   // [128][D * levels] (emb or res requested)
+    float* st_res = st_emb + (size_t)RQT_ROWS * D * a.levels;
+    const bool stage = a.emb != nullptr || a.res != nullptr;
+    const int tid = threadIdx.x;
+    const int cg = tid & 15, rg = tid >> 4;            // code group (16 codes), row group (8 rows)
+    const long long row0 = (long long)blockIdx.x * RQT_ROWS;
+    const int nrows = (int)((a.N - row0) < RQT_ROWS ? (a.N - row0) : RQT_ROWS);
+
+    // ---- residual tile: coalesced float4 reads of [128][D], transposed into rT (rows past N are zeros)
+    for (int e = tid; e < RQT_ROWS * (D / 4); e += RQ_THREADS) {
+        const int r = e / (D / 4), d4 = e % (D / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows) v = *reinterpret_cast<const float4*>(a.x + (row0 + r) * D + 4 * d4);
+        rT[(4 * d4) * RQT_RLD + r] = v.x; rT[(4 * d4 + 1) * RQT_RLD + r] = v.y;
+        rT[(4 * d4 + 2) * RQT_RLD + r] = v.z; rT[(4 * d4 + 3) * RQT_RLD + r] = v.w;
+    }
+    __syncthreads();
+    if (tid < RQT_ROWS) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < D; ++j) s = fmaf(rT[j * RQT_RLD + tid], rT[j * RQT_RLD + tid], s);
+        xn[tid] = s;
+        lossv[tid] = 0.f;
+    }
+
+    for (int l = 0; l < a.levels; ++l) {
+        __syncthreads();
+        const float* g = a.codebooks + (size_t)l * a.K * D;
+        for (int e = tid; e < a.K * (D / 4); e += RQ_THREADS) {
+            const int k = e / (D / 4), d4 = e % (D / 4);
+            const float4 v = *reinterpret_cast<const float4*>(g + (size_t)k * D + 4 * d4);
+            cT[(4 * d4) * KLD + k] = v.x; cT[(4 * d4 + 1) * KLD + k] = v.y;
+            cT[(4 * d4 + 2) * KLD + k] = v.z; cT[(4 * d4 + 3) * KLD + k] = v.w;
+        }
+        __syncthreads();
+        for (int k = tid; k < a.K; k += RQ_THREADS) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < D; ++j) s = fmaf(cT[j * KLD + k], cT[j * KLD + k], s);
+            cn[k] = s;
+        }
+        __syncthreads();
+
+        float best[8];
+        int best_k[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = INFINITY; best_k[i] = 0; }
+        // rows of this thread: rg*4 + {0..3} and 64 + rg*4 + {0..3}; codes per 256-code pass: q*64 + cg*4 + {0..3}, q = 0..3
+        for (int kb = 0; kb < a.K; kb += 256) {
+            // packed FP32 FMA (fma.rn.f32x2 -> FFMA2): two neighbouring codes per instruction, the row value broadcast to both
+            // halves; each half is an IEEE fma, so every dot product is still one fmaf chain over d
+            unsigned long long acc[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0ull;
+#pragma unroll 2
+            for (int d = 0; d < D; ++d) {
+                const float* rrow = rT + d * RQT_RLD;
+                const float* crow = cT + d * KLD + kb;
+                const float4 a0 = *reinterpret_cast<const float4*>(rrow + rg * 4);
+                const float4 a1 = *reinterpret_cast<const float4*>(rrow + 64 + rg * 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                unsigned long long a2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %1};" : "=l"(a2[i]) : "f"(av[i]));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(crow + q * 64 + cg * 4);   // codes (k, k+1), (k+2, k+3)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][2 * q]) : "l"(a2[i]), "l"(b.x));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][2 * q + 1]) : "l"(a2[i]), "l"(b.y));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float x2 = xn[(i < 4 ? 0 : 64) + rg * 4 + (i & 3)];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {            // ascending code index inside the thread: q-major, then the 4 of a chunk
+                    const int k = kb + (j >> 2) * 64 + cg * 4 + (j & 3);
+                    const unsigned long long pr = acc[i][j >> 1];
+                    const float dot = __uint_as_float((j & 1) ? (unsigned)(pr >> 32) : (unsigned)(pr & 0xffffffffull));
+                    const float dist = (x2 + cn[k]) - 2.f * dot;
+                    if (dist < best[i]) { best[i] = dist; best_k[i] = k; }
+                }
+            }
+        }
+        // the 16 code groups of a row group are the 16 lanes of a half warp: lexicographic (distance, index) minimum
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+                const int ok = __shfl_xor_sync(0xffffffffu, best_k[i], o);
+                if (ob < best[i] || (ob == best[i] && ok < best_k[i])) { best[i] = ob; best_k[i] = ok; }
+            }
+            if (cg == 0) sid[((i < 4 ? 0 : 64) + rg * 4 + (i & 3)) * a.levels + l] = best_k[i];
+        }
+        __syncthreads();
+        // residual update, one thread per row (the same serial fmaf chain as the other kernels: |r_new|^2 is next level's |r|^2)
+        if (tid < RQT_ROWS) {
+            const int k = sid[tid * a.levels + l];
+            float sq = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < D; ++j) {
+                const float e = cT[j * KLD + k];
+                float r = rT[j * RQT_RLD + tid];
+                if (stage) {
+                    st_res[((size_t)tid * D + j) * a.levels + l] = r;
+                    st_emb[((size_t)tid * D + j) * a.levels + l] = e;
+                }
+                r -= e;
+                sq = fmaf(r, r, sq);
+                rT[j * RQT_RLD + tid] = r;
+            }
+            xn[tid] = sq;
+            lossv[tid] += sq + a.commitment * sq;
+        }
+    }
+    __syncthreads();
+    // ---- outputs
+    for (int e = tid; e < nrows * a.levels; e += RQ_THREADS) a.ids[row0 * a.levels + e] = sid[e];
+    if (a.loss && tid < nrows) a.loss[row0 + tid] = lossv[tid];
+    if (a.res_out) {
+        for (int e = tid; e < nrows * D; e += RQ_THREADS) a.res_out[row0 * D + e] = rT[(e % D) * RQT_RLD + e / D];
+    }
+    if (stage) {
+        const size_t nfl = (size_t)nrows * D * a.levels;    // one contiguous span of the [N, D, levels] tensors, a multiple of 4 floats
+        for (size_t i = (size_t)tid * 4; i < nfl; i += RQ_THREADS * 4) {
+            if (a.emb) *reinterpret_cast<float4*>(a.emb + (size_t)row0 * D * a.levels + i) = *reinterpret_cast<const float4*>(st_emb + i);
+            if (a.res) *reinterpret_cast<float4*>(a.res + (size_t)row0 * D * a.levels + i) = *reinterpret_cast<const float4*>(st_res + i);
+        }
+    }
+}
+inline size_t rq_tile_smem_bytes(int D, int K, int levels, bool stage) {
+    size_t fl = (size_t)D * RQT_RLD + (size_t)D * (K + 4) + ((K + 3) & ~3) + 2 * RQT_ROWS + ((RQT_ROWS * levels + 3) & ~3);
+    if (stage) fl += (size_t)2 * RQT_ROWS * D * levels;
+    return fl * sizeof(float);
+}
+
 }  // namespace grb

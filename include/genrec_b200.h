@@ -234,6 +234,23 @@ int grb_hstu_layer_forward_f32(const grb_hstu_dims* d, const grb_hstu_layer_para
 /* y [T, D] fp32 = LayerNorm(x) in fp32 (the final norm in front of the fp32 head, hstu.py:134) */
 int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, float eps, int T, int D, float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ TIGER constrained beam step
+ * The per-step post-processing of Tiger.generate (genrec/models/tiger.py:364-441), host-bound Python loops in the reference.
+ * Trie = CSR over node ids: child_off [n_nodes + 1], child_tok / child_node [n_edges] sorted by token inside a node; root = 0,
+ * dead = -1 (genrec_b200.tiger_decode.TrieCSR builds it from valid_item_ids, the reference's build_trie, tiger.py:49-69).
+ *   grb_trie_log_softmax: logits [rows, V] -> probs, logp [rows, V] = softmax / log_softmax(masked_fill(~legal, -1e32) / temperature);
+ *       legal = vocab_offset + the children of node[row] (use_trie), or the range [vocab_offset, vocab_offset + num_embeddings) with
+ *       -inf elsewhere (use_trie = 0, tiger.py:377-381).
+ *   grb_beam_select: total = beam_logps + cand_logp, sorted descending (equal totals: lower flat index first); the first K candidates
+ *       whose token sequence is new survive; missing ones become (zeros, -1e32, root).  cand_tok are raw token ids (vocabulary index
+ *       - vocab_offset).  new_nodes / nodes NULL without a trie.  K <= 32, K * KK <= 1024. */
+int grb_trie_log_softmax(const float* logits, int rows, int V, const int32_t* node, const int32_t* child_off, const int32_t* child_tok,
+                         int n_nodes, int use_trie, int vocab_offset, int num_embeddings, float temperature, float* probs, float* logp,
+                         void* stream);
+int grb_beam_select(const int64_t* beam_seqs, const float* beam_logps, const int64_t* cand_tok, const float* cand_logp, const int32_t* nodes,
+                    const int32_t* child_off, const int32_t* child_tok, const int32_t* child_node, int n_nodes, int B, int K, int KK, int S,
+                    int64_t* new_seqs, float* new_logps, int32_t* new_nodes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ optimizer / casts */
 int grb_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
 /* torch.optim.Adam semantics on a flat buffer; state = 3 floats {step, 1-b1^step, 1-b2^step} ticked ON DEVICE. */

@@ -201,6 +201,47 @@ def golden_kats(name):
                os.path.join(OUT, name))
 
 
+def golden_tiger_decode(name, seed, B=3, K=4, num_emb=8, sem_dim=3, use_trie=True):
+    """Tiger.generate of the unmodified reference on a tiny random model; records what the decode loop consumed (per-step logits,
+    the torch.multinomial draws) and produced (final beams), so the post-processing can be replayed without the model."""
+    tg = ref_loader.ref_tiger()
+    torch.manual_seed(seed)
+    m = tg.Tiger(embedding_dim=32, attn_dim=48, dropout=0.0, num_heads=2, n_layers=2, num_item_embeddings=num_emb,
+                 num_user_embeddings=10, sem_id_dim=sem_dim).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    # a small item set with shared prefixes, a duplicate item and a first level with fewer than K distinct tokens
+    valid = torch.tensor([[1, 2, 3], [1, 2, 5], [1, 4, 0], [6, 0, 0], [6, 0, 7], [6, 3, 3], [2, 2, 2], [2, 2, 2], [1, 4, 1]])
+    N = 6
+    users = torch.randint(0, 10, (B, 1), generator=g)
+    items = torch.randint(0, num_emb, (B, N), generator=g)
+    types = torch.arange(N).remainder(sem_dim).unsqueeze(0).expand(B, -1).contiguous()
+    mask = torch.ones(B, N, dtype=torch.long)
+    mask[1, 4:] = 0
+    step_logits, draws = [], []
+    orig_step, orig_multi = m._decode_step, torch.multinomial
+
+    def rec_step(*a, **k):
+        out = orig_step(*a, **k)
+        step_logits.append(out.detach().clone())
+        return out
+
+    def rec_multi(*a, **k):
+        out = orig_multi(*a, **k)
+        draws.append(out.clone())
+        return out
+
+    m._decode_step = rec_step
+    torch.multinomial = rec_multi
+    try:
+        with torch.no_grad():
+            out = m.generate(users, items, types, mask, temperature=0.2, n_top_k_candidates=K, valid_item_ids=valid, use_trie=use_trie)
+    finally:
+        torch.multinomial = orig_multi
+    torch.save(dict(cfg=dict(B=B, K=K, num_emb=num_emb, sem_dim=sem_dim, temperature=0.2, use_trie=use_trie), valid_item_ids=valid,
+                    step_logits=step_logits, draws=draws, sem_ids=out.sem_ids.clone(), log_probas=out.log_probas.detach().clone()),
+               os.path.join(OUT, name))
+
+
 def main():
     assert ref_loader.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -212,6 +253,8 @@ def main():
     golden_sasrec("sasrec_d64h2.pt", V=50, D=64, H=2, blocks=2, F_=256, B=4, L=21, seed=60)
     golden_rqvae("rqvae_3x256x32.pt", seed=70)
     golden_kats("kats.pt")
+    golden_tiger_decode("tiger_decode_trie.pt", seed=80)
+    golden_tiger_decode("tiger_decode_notrie.pt", seed=90, use_trie=False)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -78,3 +78,19 @@ def ref_genrec_package():
         for k in [k for k in sys.modules if k == "genrec" or k.startswith("genrec.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def ref_tiger():
+    """The reference's genrec.models.tiger module (Tiger, build_trie), imported like ref_genrec_package()."""
+    _install_stubs()
+    saved = {k: v for k, v in sys.modules.items() if k == "genrec" or k.startswith("genrec.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF_ROOT)
+    try:
+        return importlib.import_module("genrec.models.tiger")
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k in [k for k in sys.modules if k == "genrec" or k.startswith("genrec.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

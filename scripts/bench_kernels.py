@@ -24,6 +24,28 @@ def timed(fn, iters=20, warm=5):
     return e0.elapsed_time(e1) / iters
 
 
+def graph_timed(fn, reps=10, iters=10):
+    """Device time per call with the launches captured in a CUDA graph (no host gaps: what a small kernel really costs)."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * iters)
+
+
 def main():
     dev = torch.device("cuda:0")
     peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
@@ -34,12 +56,18 @@ def main():
     for N in (12101, 1 << 20):
         x = torch.randn(N, 32, generator=g).to(dev)
         for aux in (False, True):
-            ms = timed(lambda: Fn.rq_residual_argmin(x, cbs, 0.25, want_aux=aux))
-            flops = 2 * 256 * 32 * 3 * N
-            byt = N * (32 * 4 + 3 * 8 + (2 * 32 * 3 * 4 + 4 if aux else 0))
-            print(json.dumps(dict(kernel="rq_residual_argmin", N=N, aux_outputs=aux, ms=ms, items_per_s=N / ms * 1e3,
-                                  fp32_tflops=flops / ms / 1e9, hbm_gbs=byt / ms / 1e6,
-                                  note="FP32 FMA bound by specification (no tensor cores); nominal B200 SIMT fp32 ~ 75 TFLOP/s")))
+            for mode in ("auto", "tile", "split", "thread"):
+                if mode == "auto":
+                    os.environ.pop("GRB_RQ", None)
+                else:
+                    os.environ["GRB_RQ"] = mode
+                ms = graph_timed(lambda: Fn.rq_residual_argmin(x, cbs, 0.25, want_aux=aux))
+                flops = 2 * 256 * 32 * 3 * N
+                byt = N * (32 * 4 + 3 * 8 + (2 * 32 * 3 * 4 + 4 if aux else 0))
+                print(json.dumps(dict(kernel="rq_residual_argmin", N=N, aux_outputs=aux, dispatch=mode, us=ms * 1e3, items_per_s=N / ms * 1e3,
+                                      fp32_tflops=flops / ms / 1e9, hbm_gbs=byt / ms / 1e6,
+                                      note="graph-captured device time; FP32 FMA bound by specification (no tensor cores)")))
+            os.environ.pop("GRB_RQ", None)
     # ---- HSTU layer fwd+bwd at cfg-3 geometry
     for (B, L, D, H) in ((16, 2048, 256, 8), (128, 200, 128, 4)):
         layer = HSTULayer(D, H, 0.0, 32, 64, 128, True).to(dev).train()

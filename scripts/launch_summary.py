@@ -2,16 +2,16 @@
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
-H = rows[hdr]; ki = H.index('Kernel Name'); vi = H.index('Metric Value'); ui = H.index('Metric Unit')
+H = rows[hdr]; ki = H.index('Kernel Name'); vi = H.index('Metric Value'); ui = H.index('Metric Unit'); mi = H.index('Metric Name')
 seq = []
 for r in rows[hdr + 1:]:
-    if len(r) > vi:
+    if len(r) > vi and r[mi] == 'gpu__time_duration.sum':
         v = float(r[vi].replace(',', '')); u = r[ui]
         v = v / 1000 if u == 'ns' else (v * 1000 if u == 'ms' else v)
         seq.append((r[ki].split('(')[0].replace('void ', '').replace('grb::', ''), v))
 # one training step = from one embed_fwd_kernel to the next
 starts = [i for i, (k, _) in enumerate(seq) if k.startswith('embed_fwd')]
-if len(starts) >= 2: seq = seq[starts[0]:starts[1]]
+if len(starts) >= 2: seq = seq[starts[-2]:starts[-1]]
 agg = collections.OrderedDict()
 for k, v in seq:
     c, t = agg.get(k, (0, 0.0)); agg[k] = (c + 1, t + v)

@@ -142,3 +142,38 @@ def test_oracle_vs_live_reference_fp64():
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     lo2, ls2 = oh.hstu_forward(ids, ts, tg, sd, 2, 2)
     assert (lo - lo2).abs().max() < 1e-12 and (ls - ls2).abs() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiger_decode_trie.pt", "tiger_decode_notrie.pt"])
+def test_tiger_decode_oracle_vs_reference_recording(golden, name):
+    """The oracle's restatement of Tiger.generate's post-processing replays the recorded logits and multinomial draws of the unmodified
+    reference to the same beams (tiger.py:364-441)."""
+    from oracle import tiger_decode as od
+    g = golden(name)
+    c = g["cfg"]
+    s, l = od.replay(g["step_logits"], g["draws"], g["valid_item_ids"], c["B"], c["K"], c["num_emb"], c["temperature"], c["use_trie"])
+    assert torch.equal(s, g["sem_ids"])
+    assert torch.equal(l, g["log_probas"])
+
+
+def test_trie_csr_equals_the_dict_trie():
+    """Host-side data format: the CSR trie holds exactly the nodes and edges of the reference's dict trie (tiger.py:49-69)."""
+    from genrec_b200.tiger_decode import TrieCSR
+    from oracle import tiger_decode as od
+    g = torch.Generator().manual_seed(0)
+    valid = torch.randint(0, 12, (300, 3), generator=g)
+    valid[10] = valid[3]
+    root = od.build_trie(valid)
+    t = TrieCSR.build(valid)
+    off, tok, child = t.child_off.tolist(), t.child_tok.tolist(), t.child_node.tolist()
+    seen = 0
+    stack = [(root, 0)]
+    while stack:
+        nd, i = stack.pop()
+        seen += 1
+        kids = sorted(nd.keys())
+        assert tok[off[i]:off[i + 1]] == kids
+        for e, k in zip(range(off[i], off[i + 1]), kids):
+            stack.append((nd[k], child[e]))
+    assert seen == t.n_nodes
+    assert TrieCSR.build(valid.view(100, 3, 3)).child_tok.tolist() == tok          # (B, T, C) input, tiger.py:58-60

@@ -67,10 +67,11 @@ def test_rq_empty_and_errors():
         Fn.rq_residual_argmin(torch.zeros(4, 32), torch.rand(3, 256, 32))
 
 
-@pytest.mark.parametrize("N,D,levels", [(12101, 32, 3), (777, 64, 5), (200_000, 32, 3)])
-def test_rq_split_kernel_equals_one_thread_per_row_kernel(N, D, levels, monkeypatch):
-    """The four-threads-per-row kernel keeps the arithmetic of the first-generation kernel (same dot-product order, same tie
-    rule): every output is bit-identical, including the staged [N, D, levels] writes."""
+@pytest.mark.parametrize("N,D,levels", [(12101, 32, 3), (777, 64, 5), (200_000, 32, 3), (129, 32, 1), (1, 32, 4)])
+def test_rq_kernel_generations_are_bit_identical(N, D, levels, monkeypatch):
+    """The register-blocked tile kernel (default where it applies: D = 32, K % 256 == 0), the four-threads-per-row kernel and the
+    first-generation one-thread-per-row kernel keep the same arithmetic (same dot-product order, same tie rule): every output is
+    bit-identical, including the staged [N, D, levels] writes and ragged last tiles."""
     import genrec_b200.functional as Fn
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(N % 997 + D)
@@ -79,13 +80,15 @@ def test_rq_split_kernel_equals_one_thread_per_row_kernel(N, D, levels, monkeypa
     cbs[0, 200] = cbs[0, 17]                       # exact ties: the first index must win in both
     cbs = cbs.to(dev)
     out = {}
-    for mode in ("split", "thread"):
+    for mode in ("tile", "split", "thread"):
         monkeypatch.setenv("GRB_RQ", mode)
         out[mode] = Fn.rq_residual_argmin(x, cbs, 0.25)
-    for a, b in zip(out["split"], out["thread"]):
-        assert torch.equal(a, b)
+    for mode in ("tile", "split"):
+        for a, b in zip(out[mode], out["thread"]):
+            assert torch.equal(a, b), mode
+    monkeypatch.delenv("GRB_RQ")
     ids_only = Fn.rq_residual_argmin(x, cbs, 0.25, want_aux=False)[0]
-    assert torch.equal(ids_only, out["split"][0])
+    assert torch.equal(ids_only, out["thread"][0])
 
 
 def test_rq_encoder_fp32_accurate_tensor_path(golden):
