@@ -72,10 +72,19 @@ int sm_count() {     // per device ordinal: a process may drive several GPUs
     }
     return n[dev];
 }
-bool ce_store_forced() {
-    static const bool v = [] { const char* e = getenv("GRB_CE"); return e && !strcmp(e, "store"); }();
+// GRB_CE = store : G' stored, dE by the TN GEMM (round-1 schedule; always at D = 256)
+//          exact : no [T, C] tensor, two class sweeps (the exponent shift is the exact row maximum)
+//          (default) : no [T, C] tensor, ONE class sweep (shift = max(probe-tile maximum, target logit), see tc_ce.cuh)
+int ce_mode_env() {
+    static const int v = [] {
+        const char* e = getenv("GRB_CE");
+        if (e && !strcmp(e, "store")) return (int)CE_STORE_G;
+        if (e && (!strcmp(e, "exact") || !strcmp(e, "keep"))) return (int)CE_KEEP_G;
+        return (int)CE_ONE_SWEEP;
+    }();
     return v;
 }
+bool ce_store_forced() { return ce_mode_env() == CE_STORE_G; }
 int row_grid(int T) {
     int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
     int cap = sm_count() * 8;
@@ -842,7 +851,7 @@ HeadWork carve_head(void* base, size_t T, size_t D, size_t C) {
     h.dxf = (float*)take(T * D * 4);
     h.scal = (float*)take(64);
     h.xs = (bf16*)take(T * D * 2);
-    h.row_sums = (float*)take(2 * T * 4);
+    h.row_sums = (float*)take(4 * T * 4);   // [2][T] sums of G' per class half, then [2][T] target-logit partials (one-sweep CE)
     h.row_stats = (float2*)take(T * 8);
     h.col_shift = (float*)take(((T + 127) / 128) * 128 * 4);
     h.ce_scratch = take(ce_scratch_bytes((int)T));
@@ -866,6 +875,10 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     // the target count (one CTA, latency-bound) depends on the targets only: with the deferred schedule it runs beside the final
     // LayerNorm and is joined before the fused CE kernel
     const bool count_aside = g_defer_on;
+    // D <= 128: no [T, C] tensor reaches HBM - dX' accumulates in TMEM beside the CE sweep and dE comes from a class-stationary pass
+    // that recomputes G.  D = 256 (or GRB_CE=store): G' is stored and dE is a TN GEMM.
+    const bool keep_g = use_tc() && D <= 128 && want_grad && !ce_store_forced();
+    const int ce_mode = keep_g ? ce_mode_env() : (int)CE_STORE_G;
     auto count = [&](cudaStream_t s_) -> int {
         launch_k(ce_count_kernel, 1, 1024, 0, s_, reinterpret_cast<const long long*>(targets), T, h.scal, loss);
         GRB_CUDA(cudaGetLastError());
@@ -879,16 +892,13 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
     if (count_aside) GRB_TRY(join_pending(st));
     else GRB_TRY(count(st));
     bool fused_dx = false;
-    // D <= 128: no [T, C] tensor reaches HBM - dX' accumulates in TMEM beside the CE sweep and dE comes from a class-stationary pass
-    // that recomputes G (GRB_CE=store keeps the round-1 schedule: G' stored, dE by the TN GEMM).  D = 256: G' is stored.
-    const bool keep_g = use_tc() && D <= 128 && want_grad && !ce_store_forced();
     if (use_tc()) {
         // fused: logits are never materialised; (D <= 128) h.dxf = G' E, and h.logits receives G' only when a dE GEMM needs it
         const long long* tg = reinterpret_cast<const long long*>(targets);                                  // (hstu.py:137-146)
         const bf16* tb = (const bf16*)table_bf16;
-        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, tb, h.logits, !keep_g, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, tb, h.logits, !keep_g, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
-        else GRB_CUDA(launch_tc_ce<4>(h.xf, tb, h.logits, true, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        if (D == 64) GRB_CUDA(launch_tc_ce<1>(h.xf, tb, h.logits, ce_mode, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else if (D == 128) GRB_CUDA(launch_tc_ce<2>(h.xf, tb, h.logits, ce_mode, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
+        else GRB_CUDA(launch_tc_ce<4>(h.xf, tb, h.logits, CE_STORE_G, T, C, h.ldl, tg, h.scal, h.row_sums, h.row_stats, h.dxf, &fused_dx, h.ce_scratch, sm_count(), st));
     } else {
     GRB_CUDA(gemm_nt_bf16(h.xf, (const bf16*)table_bf16, h.logits, h.ldl, T, C, D, st));  // logits = xf E^T   (hstu.py:137)
     if (h.ldl / 8 <= 256 * 8)
@@ -901,7 +911,8 @@ int grb_head_loss_forward_backward(const float* x, const float* ln_g, const floa
         // normalisation pass of the fused CE (rowwise.cuh ce_finish_kernel): loss, and - with gradients - dxf, x / sum_row, the one-hot
         // term of dE.  Without the dX fusion (D = 256) dxf' = G' E comes from a GEMM first.
         if (want_grad && !fused_dx) GRB_CUDA(gemm_nn_f32(h.logits, (const bf16*)table_bf16, h.dxf, nullptr, 1.f, T, D, C, h.ldl, D, st));
-        CeFinishArgs fa{h.row_sums, h.row_stats, reinterpret_cast<const long long*>(targets), h.scal, h.xf, (const bf16*)table_bf16,
+        CeFinishArgs fa{h.row_sums, h.row_stats, ce_mode == CE_ONE_SWEEP ? h.row_sums + (size_t)2 * T : nullptr,
+                        reinterpret_cast<const long long*>(targets), h.scal, h.xf, (const bf16*)table_bf16,
                         want_grad ? h.dxf : nullptr, (want_grad && !keep_g) ? h.xs : nullptr, keep_g ? h.col_shift : nullptr,
                         want_grad ? dtable : nullptr, loss, T, D};
         launch_k(ce_finish_kernel, row_grid(T), ROW_THREADS, 0, st, fa);

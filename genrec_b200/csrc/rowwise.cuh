@@ -813,7 +813,8 @@ __global__ void __launch_bounds__(256) collate_jagged_kernel(const long long* __
 // One warp per token row; rows with target 0 (ignore_index) get rs = 0 and contribute nothing.
 struct CeFinishArgs {
     const float* row_sums;       // [2][T]
-    const float2* row_stats;     // [T] {max, target logit}
+    const float2* row_stats;     // [T] {exponent shift (the row max, or the one-sweep kernel's estimate), target logit}
+    const float* tl_parts;       // nullable [2][T]: the target logit as two per-half partials (one-sweep kernel) instead of row_stats.y
     const long long* targets;    // [T]
     const float* inv_count;
     const bf16* xf;              // [T, D]
@@ -839,8 +840,9 @@ __global__ void __launch_bounds__(ROW_THREADS) ce_finish_kernel(CeFinishArgs a) 
         const float rs = (icr > 0.f && gs > 0.f) ? icr / gs : 0.f;                // 1 / sum_c exp(s_c - max)
         if (lane == 0) {
             const float2 st = a.row_stats[row];
+            const float tlog = a.tl_parts ? a.tl_parts[row] + a.tl_parts[(size_t)a.T + row] : st.y;
             const bool live = icr > 0.f && gs > 0.f;
-            if (live) lsum += (st.x + __logf(gs / icr) - st.y) * icr;
+            if (live) lsum += (st.x + __logf(gs / icr) - tlog) * icr;
             if (a.col_shift) a.col_shift[row] = live ? st.x * 1.4426950408889634f + __log2f(gs / icr) - __log2f(icr) : INFINITY;
         }
         const bf16* x = a.xf + (size_t)row * a.D;

@@ -39,7 +39,16 @@ constexpr int ce_smem_bytes() {   // fused dX (KB <= 2) keeps the table slices o
 // bf16 G' tile going to HBM; CE_ACCUM_T is the same pipeline with the operands exchanged (a block of 128 CLASS rows resident, the token
 // tiles streaming, the exponent shift a per-COLUMN array): its "dX" accumulator is dE[class, :] = sum_tokens G[token, class] x[token, :],
 // so the tied-table gradient needs no [T, C] tensor in HBM either - it recomputes S once more instead (K = D is cheap).
-enum { CE_STORE_G = 0, CE_KEEP_G = 1, CE_ACCUM_T = 2 };
+// CE_ONE_SWEEP is CE_KEEP_G without the statistics sweep: the exponent shift of a row only has to be NEAR its maximum, not equal to it
+// (the normalisation by the row sum happens later, in ce_finish_kernel), so the kernel takes
+//     shift = max( max over the first class tile ,  logit of the row's target class )
+// - the first term from ONE probe tile that both halves of a row block compute (bit-identical, no exchange between the halves), the
+// second a 128-term dot product per row.  shift <= the row maximum, so nothing underflows that the exact shift would keep; the result
+// is exact as long as no class beats BOTH the target and 128 probe classes by more than ~98 nats (fp32 / bf16 range of
+// exp(s - shift) / count) - a token whose own loss exceeds 98 nats.  Beyond that the row's G' overflows to inf and loss and gradients
+// come out inf / NaN: loud, never silently wrong; GRB_CE=exact selects the two-sweep mode, which has no such limit.
+// One S recompute and one epilogue pass less: a third of the kernel's tensor and element-wise work.
+enum { CE_STORE_G = 0, CE_KEEP_G = 1, CE_ACCUM_T = 2, CE_ONE_SWEEP = 3 };
 
 struct CeShape {
     int T, C, ldl;       // rows of the resident operand, rows of the streaming operand, leading dimension of dlogits (multiple of 8, >= C)
@@ -99,10 +108,12 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                  float* __restrict__ row_sums /* [2][T]: sum_c G'[row, c] of each class half */,
                  float2* __restrict__ row_stats /* [T]: {row max, target logit} */,
                  const float* __restrict__ col_shift /* CE_ACCUM_T: [num_n * 128] exponent shift of each streaming row (+inf = skip) */,
+                 const bf16* __restrict__ table /* CE_ONE_SWEEP: the class table [C, D] (rows gathered for the target logits) */,
                  float* __restrict__ dx_out /* [T, 64*KB] fp32 +=, written only when the second MMA is compiled in (KB <= 2) */) {
     constexpr bool FUSE_DX = KB <= 2;
     static_assert(MODE == CE_STORE_G || FUSE_DX, "without the G' store the second MMA is the only consumer of the tile");
-    constexpr int SWEEPS = MODE == CE_ACCUM_T ? 1 : 2;
+    constexpr int SWEEPS = (MODE == CE_ACCUM_T || MODE == CE_ONE_SWEEP) ? 1 : 2;
+    constexpr bool ONE = MODE == CE_ONE_SWEEP;
     constexpr int NS = KB <= 2 ? 3 * KB : 5;
     constexpr int D = 64 * KB;
     extern __shared__ unsigned char ce_smem_raw[];
@@ -165,8 +176,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 mbar_expect_tx(xfull, KB * TC_TILE_BYTES);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(sX + kb * TC_TILE_BYTES, &tmX, kb * 64, blk * 128, xfull);
                 xphase ^= 1;
-                for (int tile = 0; tile < SWEEPS * ntile; ++tile) {
-                    const int n0 = (nb + tile % ntile) * 128;
+                for (int tile = ONE ? -1 : 0; tile < SWEEPS * ntile; ++tile) {
+                    const int n0 = tile < 0 ? 0 : (nb + tile % ntile) * 128;      // tile -1: the probe (class tile 0) of CE_ONE_SWEEP
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&eempty[stage], phase ^ 1);
                         mbar_expect_tx(&efull[stage], TC_TILE_BYTES);
@@ -225,8 +236,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 tc_fence_after();
                 int prev_stage = -1, prev_buf = 0;
                 bool first_g = true;
-                for (int tile = 0; tile < SWEEPS * ntile; ++tile) {
-                    const bool sweep1 = MODE == CE_ACCUM_T || tile >= ntile;
+                for (int tile = ONE ? -1 : 0; tile < SWEEPS * ntile; ++tile) {
+                    const bool sweep1 = MODE == CE_ACCUM_T || (ONE ? tile >= 0 : tile >= ntile);
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 128;
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
         const int sub = warp & 3, cq = (warp - 2) >> 2;   // TMEM sub-partition ; 32-column quarter of the class tile
         const int r = sub * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
-        int gbuf = 0; uint32_t gphase = 0, dxphase = 0;
+        int gbuf = 0; uint32_t gphase = 0, dxphase = 0, xphase_e = 0;
         const float ic = MODE == CE_ACCUM_T ? 0.f : *inv_count;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
             int blk, nb, ne;
@@ -284,12 +295,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             const int half = w & 1;
             const int row = blk * 128 + r;
             float gshift = 0.f, g_sum = 0.f;   // exponent shift of this row ; sum of this thread's G' entries (this half, this quarter)
+            if (ONE) { mbar_wait(xfull, xphase_e); xphase_e ^= 1; }   // the epilogue reads the token tile itself (row norms)
+            int t = 0;
+            float tl = 0.f;
             if (MODE != CE_ACCUM_T) {
-            const int t = row < sh.T ? (int)targets[row] : 0;
+            t = row < sh.T ? (int)targets[row] : 0;
             const float icr = t != 0 ? ic : 0.f;   // ignore_index = 0 (and rows past the end)
-            float m_run = -INFINITY, tl = 0.f;
-            // ------------------------------------------------------------------ sweep 0: statistics
-            for (int n = nb; n < ne; ++n) {
+            float m_run = -INFINITY;
+            // ------------------------------------------------------------------ sweep 0: statistics (CE_ONE_SWEEP: the probe tile only)
+            for (int n = ONE ? 0 : nb; n < (ONE ? 1 : ne); ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 {
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                         for (int i = 0; i < 32; ++i)
                             if (col0 + i >= sh.C) v[i] = -INFINITY;
                     }
-                    if ((unsigned)(t - col0) < 32u) {
+                    if (!ONE && (unsigned)(t - col0) < 32u) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (i == t - col0) tl = v[i];
@@ -320,6 +334,25 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             // combine the four column quarters of every row (this half of the classes) ...
             s_part[(cq * 3 + 0) * 128 + r] = m_run;
             s_part[(cq * 3 + 2) * 128 + r] = tl;
+            if (ONE) {
+                // this quarter's 32 terms of x_row . E[target]: x from the resident token tile (16-byte chunk j of a row sits at
+                // j ^ (row & 7) inside its 128-byte swizzle row), E[target] from global memory (L2-resident table)
+                float dot = 0.f;
+                if (cq * 32 < D) {
+                    const bf16* erow = table + (size_t)t * D + cq * 32;
+                    const unsigned char* xrow = sX + (cq >> 1) * TC_TILE_BYTES + r * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 xu = *reinterpret_cast<const uint4*>(xrow + ((((cq & 1) * 4 + c) ^ (r & 7)) << 4));
+                        const uint4 eu = *reinterpret_cast<const uint4*>(erow + c * 8);
+                        const float2 x0 = unpack_bf16(xu.x), x1 = unpack_bf16(xu.y), x2 = unpack_bf16(xu.z), x3 = unpack_bf16(xu.w);
+                        const float2 e0 = unpack_bf16(eu.x), e1 = unpack_bf16(eu.y), e2 = unpack_bf16(eu.z), e3 = unpack_bf16(eu.w);
+                        dot = fmaf(x0.x, e0.x, dot); dot = fmaf(x0.y, e0.y, dot); dot = fmaf(x1.x, e1.x, dot); dot = fmaf(x1.y, e1.y, dot);
+                        dot = fmaf(x2.x, e2.x, dot); dot = fmaf(x2.y, e2.y, dot); dot = fmaf(x3.x, e3.x, dot); dot = fmaf(x3.y, e3.y, dot);
+                    }
+                }
+                s_part[(cq * 3 + 1) * 128 + r] = dot;
+            }
             ce_bar_sync();
             float mh = -INFINITY, tlh = 0.f;
 #pragma unroll
@@ -327,6 +360,13 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                 mh = fmaxf(mh, s_part[(q * 3 + 0) * 128 + r]);
                 tlh += s_part[(q * 3 + 2) * 128 + r];
             }
+            if (ONE) {
+                const float tdot = (s_part[1 * 128 + r] + s_part[4 * 128 + r]) + (s_part[7 * 128 + r] + s_part[10 * 128 + r]);
+                const float mm = fmaxf(mh, tdot);
+                gshift = mm * kLog2e - __log2f(icr);
+                if (half == 0 && cq == 0 && row < sh.T) row_stats[row] = make_float2(mm, 0.f);
+                tl = 0.f;
+            } else {
             // ... publish them, and pick up the partner item's maximum: both halves must scale their exponentials alike, their dX'
             // partials and G' tiles are summed
             if (cq == 0) sh.stats[(size_t)w * 128 + r] = make_float4(mh, 0.f, tlh, 0.f);
@@ -341,6 +381,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             const float mm = fmaxf(mh, pp.x);
             gshift = mm * kLog2e - __log2f(icr);               // icr == 0 (ignored row) -> +inf -> every entry of G' is 2^-inf = 0
             if (half == 0 && cq == 0 && row < sh.T) row_stats[row] = make_float2(mm, tlh + pp.z);
+            }
             }
             // ------------------------------------------------------------------ sweep 1: gradient tiles
             if (MODE == CE_STORE_G && warp == 2 && lane == 0) tma_store_wait_read();  // both staging buffers are free of pending bulk stores
@@ -359,6 +400,11 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained (it lives in registers now)
                     const int col0 = n * 128 + cq * 32;
+                    if (ONE && (unsigned)(t - col0) < 32u) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i == t - col0) tl = v[i];
+                    }
                     if (MODE == CE_ACCUM_T) {   // the shift belongs to the streaming (token) row = this tile's column
                         const float4* cs = reinterpret_cast<const float4*>(col_shift + col0);
 #pragma unroll
@@ -425,9 +471,14 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
             // row sums of this half -> global (four quarters combined through shared memory; slot 1 of s_part is free now)
             if (MODE != CE_ACCUM_T) {
                 s_part[(cq * 3 + 1) * 128 + r] = g_sum;
+                if (ONE) s_part[(cq * 3 + 2) * 128 + r] = tl;
                 ce_bar_sync();
-                if (cq == 0 && row < sh.T)
+                if (cq == 0 && row < sh.T) {
                     row_sums[(size_t)half * sh.T + row] = (s_part[1 * 128 + r] + s_part[4 * 128 + r]) + (s_part[7 * 128 + r] + s_part[10 * 128 + r]);
+                    if (ONE)   // target logit of this half's classes (0 when the target lives in the other half)
+                        row_sums[(size_t)(2 + half) * sh.T + row] = (s_part[2 * 128 + r] + s_part[5 * 128 + r]) + (s_part[8 * 128 + r] + s_part[11 * 128 + r]);
+                }
+                if (ONE) ce_bar_sync();   // the next item's probe reuses slots 1 and 2 of s_part
             }
             if (FUSE_DX && ne > nb) {
                 // ------------------------------------------------------------------ dX' partial of this half: TMEM -> += fp32 global
@@ -476,13 +527,16 @@ inline cudaError_t ce_set_attr() {
     return cudaSuccess;
 }
 // scratch: ce_scratch_bytes(T) bytes of device memory (partials + flags); dx must hold [T, D] fp32 and is zero-filled here
+// mode: CE_STORE_G, CE_KEEP_G or CE_ONE_SWEEP (the latter two need D <= 128; row_sums must be [4][T] for CE_ONE_SWEEP: sums of the two
+// halves, then their target-logit partials)
 template <int KB>
-inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, bool store_g, int T, int C, int ldl, const long long* targets,
+inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, int mode, int T, int C, int ldl, const long long* targets,
                                 const float* inv_count, float* row_sums, float2* row_stats, float* dx, bool* fused_dx, void* scratch,
                                 int num_sms, cudaStream_t st) {
     CUtensorMap tmX, tmE, tmG;
     const int D = 64 * KB;
-    if (KB > 2) store_g = true;
+    if (KB > 2) mode = CE_STORE_G;
+    const bool store_g = mode == CE_STORE_G;
     bool ok = make_tmap_bf16(&tmX, X, T, D, D, 64, 128) && make_tmap_bf16(&tmE, E, C, D, D, 64, 128) && make_tmap(&tmG, G, false, T, ldl, ldl, 64, 128);
     if (!ok) return cudaErrorInvalidValue;
     CeShape sh;
@@ -493,7 +547,8 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, bool stor
     sh.nsplit = 2;
     sh.stats = reinterpret_cast<float4*>(scratch);
     sh.flags = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)2 * sh.num_m * 128 * sizeof(float4));
-    cudaError_t me = cudaMemsetAsync(sh.flags, 0, (size_t)2 * sh.num_m * sizeof(unsigned), st);
+    cudaError_t me = cudaSuccess;
+    if (mode != CE_ONE_SWEEP) me = cudaMemsetAsync(sh.flags, 0, (size_t)2 * sh.num_m * sizeof(unsigned), st);
     if (me != cudaSuccess) return me;
     *fused_dx = KB <= 2;
     if (KB <= 2) {
@@ -506,13 +561,20 @@ inline cudaError_t launch_tc_ce(const bf16* X, const bf16* E, bf16* G, bool stor
         me = ce_set_attr<KB, CE_STORE_G>();
         if (me != cudaSuccess) return me;
         launch_k(tc_ce_kernel<KB, CE_STORE_G>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums,
-                 row_stats, (const float*)nullptr, dx);
+                 row_stats, (const float*)nullptr, E, dx);
+    } else if (mode == CE_ONE_SWEEP) {
+        constexpr int M = KB <= 2 ? CE_ONE_SWEEP : CE_STORE_G;
+        me = ce_set_attr<KB, M>();
+        if (me != cudaSuccess) return me;
+        grid = 2 * sh.num_m < num_sms ? 2 * sh.num_m : num_sms;     // no exchange between the halves: any grid will do
+        launch_k(tc_ce_kernel<KB, M>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums, row_stats,
+                 (const float*)nullptr, E, dx);
     } else {
         constexpr int M = KB <= 2 ? CE_KEEP_G : CE_STORE_G;
         me = ce_set_attr<KB, M>();
         if (me != cudaSuccess) return me;
         launch_k(tc_ce_kernel<KB, M>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmX, tmE, tmG, sh, targets, inv_count, row_sums, row_stats,
-                 (const float*)nullptr, dx);
+                 (const float*)nullptr, E, dx);
     }
     return cudaGetLastError();
 }
@@ -549,7 +611,7 @@ inline cudaError_t launch_tc_ce_accum_t(const bf16* X, const bf16* E, const floa
     const int items = sh.num_m * sh.nsplit;
     const int grid = items < num_sms ? items : num_sms;
     launch_k(tc_ce_kernel<KB, CE_ACCUM_T>, grid, CE_THREADS, ce_smem_bytes<KB>(), st, tmRes, tmStream, tmStream, sh, (const long long*)nullptr,
-             (const float*)nullptr, (float*)nullptr, (float2*)nullptr, col_shift, dE);
+             (const float*)nullptr, (float*)nullptr, (float2*)nullptr, col_shift, (const bf16*)nullptr, dE);
     return cudaGetLastError();
 }
 

@@ -116,14 +116,51 @@ class _AttnFn(torch.autograd.Function):
         return dq, dkv, None, None, None, dwq, dbq, dwk, dbk, dwv, dbv
 
 
+class _FfnFn(torch.autograd.Function):
+    """PointWiseFeedForward.forward as a unit (sasrec.py:258-266): fc1 + ReLU + dropout, fc2 + dropout + residual - the same two
+    fused-epilogue GEMMs the block path runs."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, w1, b1, w2, b2):
+        require_cuda(x, residual)
+        ensure_device(x.device)
+        xf = x.detach().contiguous().float()
+        res = residual.detach().contiguous().float()
+        w1b, w2b = Fn.cast_bf16(w1), Fn.cast_bf16(w2)
+        xb = Fn.cast_rows_bf16(xf)
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF if p > 0 else 0
+        z1, a1 = Fn.linear_fwd(xb, w1b, b1.detach(), 2, p, seed, None, SITE_HID)
+        y = Fn.linear_residual_fwd(a1, w2b, b2.detach(), res, None, p, seed, None, SITE_OUT)
+        ctx.save_for_backward(xb, z1, a1, w1b, w2b)
+        ctx.cfg = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, z1, a1, w1b, w2b = ctx.saved_tensors
+        p, seed = ctx.cfg
+        dy = dy.contiguous().float()
+        dyb = Fn.cast_rows_bf16(dy, None, p, seed, None, SITE_OUT)
+        _, dw2, db2 = Fn.linear_bwd(dyb, w2b, a1, need_dx=False)
+        dz1 = Fn.linear_dact_bwd(dyb, w2b, z1, 2, p, seed, None, SITE_HID)
+        dx, dw1, db1 = Fn.linear_bwd(dz1, w1b, xb)
+        return dx, dy, None, dw1, db1, dw2, db2
+
+
 class PointWiseFeedForward(nn.Module):
-    """Mirror of genrec/models/sasrec.py:249-266 (parameter container; the fused block path runs it)."""
+    """Mirror of genrec/models/sasrec.py:249-266.  Inside a SASRecBlock the fused block path runs it; called on its own it is the
+    same pair of kernels behind an autograd function."""
 
     def __init__(self, embed_dim: int, ffn_dim: int, dropout: float):
         super().__init__()
         self.fc1 = nn.Linear(embed_dim, ffn_dim)
         self.fc2 = nn.Linear(ffn_dim, embed_dim)
         self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        """x: normalised input [B, L, D]; residual: the block input [B, L, D]  ->  fc2(drop(relu(fc1(x)))) dropped + residual."""
+        return _FfnFn.apply(x, residual, self.dropout.p if self.training else 0.0, self.fc1.weight, self.fc1.bias, self.fc2.weight,
+                            self.fc2.bias)
 
 
 class SASRecBlock(nn.Module):
