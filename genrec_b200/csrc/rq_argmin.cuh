@@ -323,20 +323,21 @@ __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_split_kernel(Rq
 // and the distance is still (|r|^2 + |c|^2) - 2 r.c with strict '<' over ascending code indices, so ids are bit-identical to the
 // kernels above (tests/test_rq_gpu.py).  The 16 threads that share a row meet through 4 shuffle steps (lower index wins ties).
 // Outputs in the reference's [N, D, levels] layout are staged per tile and written as one contiguous span.
-constexpr int RQT_ROWS = 128;             // rows per CTA
-constexpr int RQT_RLD = RQT_ROWS + 4;     // row pitch of the transposed tiles (floats); +4 keeps 16-byte alignment of the float4 loads
+constexpr int RQT_ROWS = 64;              // rows per CTA
+constexpr int RQT_THREADS = 128;          // 16 code groups x 8 row groups; 255 registers -> two CTAs per SM overlap each other's serial phases
+constexpr int RQT_RLD = RQT_ROWS + 4;     // row pitch of the transposed residual tile (floats); +4 keeps the float4 loads 16-byte aligned
 template <int D>
-__global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(RqArgs a) {
+__global__ void __launch_bounds__(RQT_THREADS, 2) rq_residual_argmin_tile_kernel(RqArgs a) {
     pdl_wait();
     extern __shared__ __align__(16) float rq_smem[];
     const int KLD = a.K + 4;
     float* rT = rq_smem;                               // [D][RQT_RLD]   residual, transposed
     float* cT = rT + D * RQT_RLD;                      // [D][KLD]       codebook level, transposed
     float* cn = cT + D * KLD;                          // [K]            |c|^2
-    float* xn = cn + ((a.K + 3) & ~3);                 // [128]          |r|^2
-    float* lossv = xn + RQT_ROWS;                      // [128]
-    int* sid = reinterpret_cast<int*>(lossv + RQT_ROWS);          // [128][levels] chosen codes
-    float* st_emb = reinterpret_cast<float*>(sid + RQT_ROWS * a.levels + ((4 - (RQT_ROWS * a.levels) % 4) % 4));   // [128][D * levels] (emb or res requested)
+    float* xn = cn + ((a.K + 3) & ~3);                 // [rows]         |r|^2
+    float* lossv = xn + RQT_ROWS;                      // [rows]
+    int* sid = reinterpret_cast<int*>(lossv + RQT_ROWS);          // [rows][levels] chosen codes
+    float* st_emb = reinterpret_cast<float*>(sid + ((RQT_ROWS * a.levels + 3) & ~3));   // [rows][D * levels] (emb or res requested)
     float* st_res = st_emb + (size_t)RQT_ROWS * D * a.levels;
     const bool stage = a.emb != nullptr || a.res != nullptr;
     const int tid = threadIdx.x;
@@ -344,9 +345,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
     const long long row0 = (long long)blockIdx.x * RQT_ROWS;
     const int nrows = (int)((a.N - row0) < RQT_ROWS ? (a.N - row0) : RQT_ROWS);
 
-    // ---- residual tile: coalesced float4 reads of [128][D], transposed into rT (rows past N are zeros)
-    for (int e = tid; e < RQT_ROWS * (D / 4); e += RQ_THREADS) {
-        const int r = e / (D / 4), d4 = e % (D / 4);
+    // ---- residual tile: float4 reads of [rows][D], transposed into rT (rows past N are zeros).  Lanes run along the rows so the
+    //      transposed stores hit consecutive banks; the global side re-reads each 128-byte row from L1.
+    for (int e = tid; e < RQT_ROWS * (D / 4); e += RQT_THREADS) {
+        const int r = e % RQT_ROWS, d4 = e / RQT_ROWS;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nrows) v = *reinterpret_cast<const float4*>(a.x + (row0 + r) * D + 4 * d4);
         rT[(4 * d4) * RQT_RLD + r] = v.x; rT[(4 * d4 + 1) * RQT_RLD + r] = v.y;
@@ -364,14 +366,14 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
     for (int l = 0; l < a.levels; ++l) {
         __syncthreads();
         const float* g = a.codebooks + (size_t)l * a.K * D;
-        for (int e = tid; e < a.K * (D / 4); e += RQ_THREADS) {
-            const int k = e / (D / 4), d4 = e % (D / 4);
+        for (int e = tid; e < a.K * (D / 4); e += RQT_THREADS) {
+            const int k = e % a.K, d4 = e / a.K;          // lanes along the codes: conflict-free transposed stores
             const float4 v = *reinterpret_cast<const float4*>(g + (size_t)k * D + 4 * d4);
             cT[(4 * d4) * KLD + k] = v.x; cT[(4 * d4 + 1) * KLD + k] = v.y;
             cT[(4 * d4 + 2) * KLD + k] = v.z; cT[(4 * d4 + 3) * KLD + k] = v.w;
         }
         __syncthreads();
-        for (int k = tid; k < a.K; k += RQ_THREADS) {
+        for (int k = tid; k < a.K; k += RQT_THREADS) {
             float s = 0.f;
 #pragma unroll 8
             for (int j = 0; j < D; ++j) s = fmaf(cT[j * KLD + k], cT[j * KLD + k], s);
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
         int best_k[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { best[i] = INFINITY; best_k[i] = 0; }
-        // rows of this thread: rg*4 + {0..3} and 64 + rg*4 + {0..3}; codes per 256-code pass: q*64 + cg*4 + {0..3}, q = 0..3
+        // rows of this thread: rg*8 + {0..7}; codes per 256-code pass: q*64 + cg*4 + {0..3}, q = 0..3
         for (int kb = 0; kb < a.K; kb += 256) {
             // packed FP32 FMA (fma.rn.f32x2 -> FFMA2): two neighbouring codes per instruction, the row value broadcast to both
             // halves; each half is an IEEE fma, so every dot product is still one fmaf chain over d
@@ -394,10 +396,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
                 for (int j = 0; j < 8; ++j) acc[i][j] = 0ull;
 #pragma unroll 2
             for (int d = 0; d < D; ++d) {
-                const float* rrow = rT + d * RQT_RLD;
+                const float* rrow = rT + d * RQT_RLD + rg * 8;
                 const float* crow = cT + d * KLD + kb;
-                const float4 a0 = *reinterpret_cast<const float4*>(rrow + rg * 4);
-                const float4 a1 = *reinterpret_cast<const float4*>(rrow + 64 + rg * 4);
+                const float4 a0 = *reinterpret_cast<const float4*>(rrow);
+                const float4 a1 = *reinterpret_cast<const float4*>(rrow + 4);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 unsigned long long a2[8];
 #pragma unroll
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float x2 = xn[(i < 4 ? 0 : 64) + rg * 4 + (i & 3)];
+                const float x2 = xn[rg * 8 + i];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {            // ascending code index inside the thread: q-major, then the 4 of a chunk
                     const int k = kb + (j >> 2) * 64 + cg * 4 + (j & 3);
@@ -434,22 +436,26 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
                 const int ok = __shfl_xor_sync(0xffffffffu, best_k[i], o);
                 if (ob < best[i] || (ob == best[i] && ok < best_k[i])) { best[i] = ob; best_k[i] = ok; }
             }
-            if (cg == 0) sid[((i < 4 ? 0 : 64) + rg * 4 + (i & 3)) * a.levels + l] = best_k[i];
+            if (cg == 0) sid[(rg * 8 + i) * a.levels + l] = best_k[i];
         }
         __syncthreads();
+        if (stage) {
+            // residual BEFORE the level and the chosen code word -> staging, all threads, lanes along d (stride `levels` in the
+            // [row][d][level] layout: conflict-free for levels coprime with 32, e.g. 3)
+            for (int e = tid; e < RQT_ROWS * D; e += RQT_THREADS) {
+                const int r = e / D, j = e % D;
+                st_res[(size_t)e * a.levels + l] = rT[j * RQT_RLD + r];
+                st_emb[(size_t)e * a.levels + l] = cT[j * KLD + sid[r * a.levels + l]];
+            }
+            __syncthreads();
+        }
         // residual update, one thread per row (the same serial fmaf chain as the other kernels: |r_new|^2 is next level's |r|^2)
         if (tid < RQT_ROWS) {
             const int k = sid[tid * a.levels + l];
             float sq = 0.f;
 #pragma unroll 8
             for (int j = 0; j < D; ++j) {
-                const float e = cT[j * KLD + k];
-                float r = rT[j * RQT_RLD + tid];
-                if (stage) {
-                    st_res[((size_t)tid * D + j) * a.levels + l] = r;
-                    st_emb[((size_t)tid * D + j) * a.levels + l] = e;
-                }
-                r -= e;
+                float r = rT[j * RQT_RLD + tid] - cT[j * KLD + k];
                 sq = fmaf(r, r, sq);
                 rT[j * RQT_RLD + tid] = r;
             }
@@ -459,14 +465,14 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_residual_argmin_tile_kernel(
     }
     __syncthreads();
     // ---- outputs
-    for (int e = tid; e < nrows * a.levels; e += RQ_THREADS) a.ids[row0 * a.levels + e] = sid[e];
+    for (int e = tid; e < nrows * a.levels; e += RQT_THREADS) a.ids[row0 * a.levels + e] = sid[e];
     if (a.loss && tid < nrows) a.loss[row0 + tid] = lossv[tid];
     if (a.res_out) {
-        for (int e = tid; e < nrows * D; e += RQ_THREADS) a.res_out[row0 * D + e] = rT[(e % D) * RQT_RLD + e / D];
+        for (int e = tid; e < nrows * D; e += RQT_THREADS) a.res_out[row0 * D + e] = rT[(e % D) * RQT_RLD + e / D];
     }
     if (stage) {
         const size_t nfl = (size_t)nrows * D * a.levels;    // one contiguous span of the [N, D, levels] tensors, a multiple of 4 floats
-        for (size_t i = (size_t)tid * 4; i < nfl; i += RQ_THREADS * 4) {
+        for (size_t i = (size_t)tid * 4; i < nfl; i += RQT_THREADS * 4) {
             if (a.emb) *reinterpret_cast<float4*>(a.emb + (size_t)row0 * D * a.levels + i) = *reinterpret_cast<const float4*>(st_emb + i);
             if (a.res) *reinterpret_cast<float4*>(a.res + (size_t)row0 * D * a.levels + i) = *reinterpret_cast<const float4*>(st_res + i);
         }
