@@ -1363,7 +1363,7 @@ int grb_rq_residual_argmin(const float* x, const float* codebooks, int64_t N, in
     {
         const bool stage = emb != nullptr || res != nullptr;
         const size_t smem = rq_tile_smem_bytes(D, K, levels, stage);
-        if (!force_thread && !force_split && D == 32 && K % 256 == 0 && smem <= 110 * 1024) {
+        if (!force_thread && !force_split && D == 32 && K % 256 == 0 && smem <= 220 * 1024) {
             GRB_TRY(set_smem(rq_residual_argmin_tile_kernel<32>, smem));
             const unsigned grid = (unsigned)((N + RQT_ROWS - 1) / RQT_ROWS);
             launch_k(rq_residual_argmin_tile_kernel<32>, grid, RQT_THREADS, smem, st, a);

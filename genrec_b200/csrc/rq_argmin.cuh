@@ -323,11 +323,12 @@ __global__ void __launch_bounds__(RQ_THREADS) rq_residual_argmin_split_kernel(Rq
 // and the distance is still (|r|^2 + |c|^2) - 2 r.c with strict '<' over ascending code indices, so ids are bit-identical to the
 // kernels above (tests/test_rq_gpu.py).  The 16 threads that share a row meet through 4 shuffle steps (lower index wins ties).
 // Outputs in the reference's [N, D, levels] layout are staged per tile and written as one contiguous span.
-constexpr int RQT_ROWS = 64;              // rows per CTA
-constexpr int RQT_THREADS = 128;          // 16 code groups x 8 row groups; 255 registers -> two CTAs per SM overlap each other's serial phases
+constexpr int RQT_ROWS = 128;             // rows per CTA (64 rows / 128 threads / two CTAs per SM measured slower without the auxiliary
+                                          // outputs: 1.78 vs 1.58 ms at N = 2^20 - every CTA transposes the level's codebook for itself)
+constexpr int RQT_THREADS = 256;          // 16 code groups x 16 row groups
 constexpr int RQT_RLD = RQT_ROWS + 4;     // row pitch of the transposed residual tile (floats); +4 keeps the float4 loads 16-byte aligned
 template <int D>
-__global__ void __launch_bounds__(RQT_THREADS, 2) rq_residual_argmin_tile_kernel(RqArgs a) {
+__global__ void __launch_bounds__(RQT_THREADS, 1) rq_residual_argmin_tile_kernel(RqArgs a) {
     pdl_wait();
     extern __shared__ __align__(16) float rq_smem[];
     const int KLD = a.K + 4;
@@ -345,10 +346,9 @@ __global__ void __launch_bounds__(RQT_THREADS, 2) rq_residual_argmin_tile_kernel
     const long long row0 = (long long)blockIdx.x * RQT_ROWS;
     const int nrows = (int)((a.N - row0) < RQT_ROWS ? (a.N - row0) : RQT_ROWS);
 
-    // ---- residual tile: float4 reads of [rows][D], transposed into rT (rows past N are zeros).  Lanes run along the rows so the
-    //      transposed stores hit consecutive banks; the global side re-reads each 128-byte row from L1.
+    // ---- residual tile: coalesced float4 reads of [rows][D], transposed into rT (rows past N are zeros)
     for (int e = tid; e < RQT_ROWS * (D / 4); e += RQT_THREADS) {
-        const int r = e % RQT_ROWS, d4 = e / RQT_ROWS;
+        const int r = e / (D / 4), d4 = e % (D / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nrows) v = *reinterpret_cast<const float4*>(a.x + (row0 + r) * D + 4 * d4);
         rT[(4 * d4) * RQT_RLD + r] = v.x; rT[(4 * d4 + 1) * RQT_RLD + r] = v.y;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(RQT_THREADS, 2) rq_residual_argmin_tile_kernel
         __syncthreads();
         const float* g = a.codebooks + (size_t)l * a.K * D;
         for (int e = tid; e < a.K * (D / 4); e += RQT_THREADS) {
-            const int k = e % a.K, d4 = e / a.K;          // lanes along the codes: conflict-free transposed stores
+            const int k = e / (D / 4), d4 = e % (D / 4);
             const float4 v = *reinterpret_cast<const float4*>(g + (size_t)k * D + 4 * d4);
             cT[(4 * d4) * KLD + k] = v.x; cT[(4 * d4 + 1) * KLD + k] = v.y;
             cT[(4 * d4 + 2) * KLD + k] = v.z; cT[(4 * d4 + 3) * KLD + k] = v.w;
