@@ -11,6 +11,7 @@
 
 #include "attn_hstu.cuh"
 #include "attn_sasrec.cuh"
+#include "attn_t5.cuh"
 #include "attn_tc.cuh"
 #include "beam.cuh"
 #include "common.cuh"
@@ -1236,6 +1237,71 @@ int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, fl
     if (D == 64) launch_k(ln_f32_kernel<2>, grid, 256, 0, st, x, g, b, y, T, eps);
     else if (D == 128) launch_k(ln_f32_kernel<4>, grid, 256, 0, st, x, g, b, y, T, eps);
     else launch_k(ln_f32_kernel<8>, grid, 256, 0, st, x, g, b, y, T, eps);
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ T5-style attention core (TIGER)
+static int t5_args(T5AttnArgs& a, const void* q, const void* k, const void* v, int B, int Lq, int Lk, int H, int DH, int ldq, int ldk, int ldv,
+                   const float* bias, const int32_t* bucket, int nb, const uint8_t* key_pad, int causal, float scale, float p, uint64_t seed,
+                   const uint64_t* seed_dev, uint32_t site) {
+    GRB_REQUIRE(q && k && v, "null argument");
+    GRB_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && H > 0 && (DH == 32 || DH == 64), "bad shape B=%d Lq=%d Lk=%d H=%d head_dim=%d", B, Lq, Lk, H, DH);
+    GRB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && aligned16(q) && aligned16(k) && aligned16(v), "rows must be 16-byte aligned");
+    GRB_REQUIRE((bias == nullptr) == (bucket == nullptr) && (!bias || (nb > 0 && nb <= 1024)), "bias table and bucket map go together");
+    GRB_REQUIRE(p >= 0.f && p < 1.f, "dropout_p out of range");
+    memset(&a, 0, sizeof(a));
+    a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
+    a.B = B; a.Lq = Lq; a.Lk = Lk; a.H = H; a.bias = bias; a.bucket = bucket; a.nb = bias ? nb : 0; a.key_pad = key_pad; a.causal = causal;
+    a.scale = scale; a.drop = make_dropout(p, seed, site, seed_dev);
+    return 0;
+}
+int grb_t5_attention_forward(const void* q, const void* k, const void* v, int B, int Lq, int Lk, int H, int head_dim, int ldq, int ldk, int ldv,
+                             const float* bias, const int32_t* bucket, int num_buckets, const uint8_t* key_pad, int causal, float scale,
+                             float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* out, int ldo, float* lse,
+                             void* stream) {
+    T5AttnArgs a;
+    GRB_TRY(t5_args(a, q, k, v, B, Lq, Lk, H, head_dim, ldq, ldk, ldv, bias, bucket, num_buckets, key_pad, causal, scale, dropout_p, seed, seed_dev, site));
+    GRB_REQUIRE(out && lse && ldo % 8 == 0 && aligned16(out), "bad output");
+    a.out = (bf16*)out; a.ldo = ldo; a.lse = lse;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((Lq + T5_ROWS - 1) / T5_ROWS, B * H);
+    if (head_dim == 32) {
+        const size_t smem = t5_fwd_smem<32>(a.nb);
+        GRB_TRY(set_smem(t5_attn_fwd_kernel<32>, smem));
+        launch_k(t5_attn_fwd_kernel<32>, grid, T5_THREADS, smem, st, a);
+    } else {
+        const size_t smem = t5_fwd_smem<64>(a.nb);
+        GRB_TRY(set_smem(t5_attn_fwd_kernel<64>, smem));
+        launch_k(t5_attn_fwd_kernel<64>, grid, T5_THREADS, smem, st, a);
+    }
+    GRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int grb_t5_attention_backward(const void* q, const void* k, const void* v, int B, int Lq, int Lk, int H, int head_dim, int ldq, int ldk, int ldv,
+                              const float* bias, const int32_t* bucket, int num_buckets, const uint8_t* key_pad, int causal, float scale,
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, const void* out, int ldo,
+                              const float* lse, const void* dout, int lddo, void* dq, int lddq, float* dk, float* dv, float* dbias,
+                              void* stream) {
+    T5AttnArgs a;
+    GRB_TRY(t5_args(a, q, k, v, B, Lq, Lk, H, head_dim, ldq, ldk, ldv, bias, bucket, num_buckets, key_pad, causal, scale, dropout_p, seed, seed_dev, site));
+    GRB_REQUIRE(out && lse && dout && dq && dk && dv && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0, "bad argument");
+    GRB_REQUIRE(aligned16(out) && aligned16(dout) && aligned16(dq), "rows must be 16-byte aligned");
+    a.out = (bf16*)const_cast<void*>(out); a.ldo = ldo; a.lse = const_cast<float*>(lse); a.dout = (const bf16*)dout; a.lddo = lddo;
+    a.dq = (bf16*)dq; a.lddq = lddq; a.dk = dk; a.dv = dv; a.dbias = bias ? dbias : nullptr;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GRB_CUDA(cudaMemsetAsync(dk, 0, (size_t)B * Lk * H * head_dim * sizeof(float), st));
+    GRB_CUDA(cudaMemsetAsync(dv, 0, (size_t)B * Lk * H * head_dim * sizeof(float), st));
+    dim3 grid((Lq + T5_ROWS - 1) / T5_ROWS, B * H);
+    if (head_dim == 32) {
+        const size_t smem = t5_bwd_smem<32>(a.nb);
+        GRB_TRY(set_smem(t5_attn_bwd_kernel<32>, smem));
+        launch_k(t5_attn_bwd_kernel<32>, grid, T5_THREADS, smem, st, a);
+    } else {
+        const size_t smem = t5_bwd_smem<64>(a.nb);
+        GRB_TRY(set_smem(t5_attn_bwd_kernel<64>, smem));
+        launch_k(t5_attn_bwd_kernel<64>, grid, T5_THREADS, smem, st, a);
+    }
     GRB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -234,6 +234,23 @@ int grb_hstu_layer_forward_f32(const grb_hstu_dims* d, const grb_hstu_layer_para
 /* y [T, D] fp32 = LayerNorm(x) in fp32 (the final norm in front of the fp32 head, hstu.py:134) */
 int grb_layernorm_f32_forward(const float* x, const float* g, const float* b, float eps, int T, int D, float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ T5-style attention core (TIGER)
+ * The score / softmax / value part of T5Attention.forward (genrec/modules/transformer.py:133-156), between the q / k / v and the
+ * output projections:  softmax((q k^T) scale + rel_bias[h, bucket(j - i)], key padding -> -1e9, causal -> -inf) with dropout on
+ * the weights, times v.  q [B, Lq, ldq], k / v [B, Lk, ld] and out are bf16 with head h in columns h*head_dim .. ; bias [H,
+ * num_buckets] fp32 with bucket [Lq + Lk - 1] int32 = the bucket of delta = j - i at index delta + Lq - 1 (both NULL for
+ * cross-attention); key_pad [B, Lk] 1 = padded (NULL: none); lse [B, H, Lq, 2] = {row max, sum of exp(s - max)} is saved for the backward.
+ * Backward: dq bf16 [B, Lq, lddq]; dk, dv fp32 [B, Lk, H * head_dim] (zero-filled here, then accumulated); dbias [H, num_buckets] +=. */
+int grb_t5_attention_forward(const void* q, const void* k, const void* v, int B, int Lq, int Lk, int H, int head_dim, int ldq, int ldk, int ldv,
+                             const float* bias, const int32_t* bucket, int num_buckets, const uint8_t* key_pad, int causal, float scale,
+                             float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* out, int ldo, float* lse,
+                             void* stream);
+int grb_t5_attention_backward(const void* q, const void* k, const void* v, int B, int Lq, int Lk, int H, int head_dim, int ldq, int ldk, int ldv,
+                              const float* bias, const int32_t* bucket, int num_buckets, const uint8_t* key_pad, int causal, float scale,
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, const void* out, int ldo,
+                              const float* lse, const void* dout, int lddo, void* dq, int lddq, float* dk, float* dv, float* dbias,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------ TIGER constrained beam step
  * The per-step post-processing of Tiger.generate (genrec/models/tiger.py:364-441), host-bound Python loops in the reference.
  * Trie = CSR over node ids: child_off [n_nodes + 1], child_tok / child_node [n_edges] sorted by token inside a node; root = 0,

@@ -242,6 +242,37 @@ def golden_tiger_decode(name, seed, B=3, K=4, num_emb=8, sem_dim=3, use_trie=Tru
                os.path.join(OUT, name))
 
 
+def golden_t5_attention(name, seed, D=64, H=2, B=3, Lq=37, Lk=21):
+    """T5Attention of the unmodified reference: encoder self-attention with key padding, decoder self-attention with the causal mask,
+    cross-attention with memory padding - outputs and every gradient, fp32."""
+    tr = ref_loader.ref_transformer()
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    cases = {}
+    for case, cross, q_len, k_len, causal in (("encoder", False, Lq, Lq, False), ("decoder", False, 9, 9, True), ("cross", True, 9, Lk, False)):
+        heads = 1 if case == "decoder" else H          # head_dim 64 in the decoder case, 32 in the others
+        m = tr.T5Attention(D, heads, dropout=0.0, is_cross_attention=cross).eval()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * (0.5 if p.shape[-1] == 1 else 0.09))
+        x = torch.randn(B, q_len, D, generator=g, requires_grad=True)
+        ctx = torch.randn(B, k_len, D, generator=g, requires_grad=True) if cross else None
+        pad = torch.zeros(B, k_len, dtype=torch.bool)
+        pad[1, k_len - 5:] = True
+        if case == "encoder":
+            pad[2, :] = True                     # a fully padded sequence: the reference's softmax is uniform there
+        if case == "decoder":
+            pad = None
+        mask = torch.nn.Transformer.generate_square_subsequent_mask(q_len) if causal else None
+        out, _ = m(x, ctx, ctx, attn_mask=mask, key_padding_mask=pad)
+        dy = torch.randn(out.shape, generator=g)
+        out.backward(dy)
+        cases[case] = dict(cross=cross, causal=causal, heads=heads, state_dict={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x.detach().clone(),
+                           ctx=ctx.detach().clone() if cross else None, pad=pad, dy=dy, out=out.detach().clone(), dx=x.grad.clone(),
+                           dctx=ctx.grad.clone() if cross else None, grads={n: p.grad.clone() for n, p in m.named_parameters()})
+    torch.save(dict(cfg=dict(D=D, H=H), cases=cases), os.path.join(OUT, name))
+
+
 def main():
     assert ref_loader.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -253,6 +284,7 @@ def main():
     golden_sasrec("sasrec_d64h2.pt", V=50, D=64, H=2, blocks=2, F_=256, B=4, L=21, seed=60)
     golden_rqvae("rqvae_3x256x32.pt", seed=70)
     golden_kats("kats.pt")
+    golden_t5_attention("t5_attention.pt", seed=100)
     golden_tiger_decode("tiger_decode_trie.pt", seed=80)
     golden_tiger_decode("tiger_decode_notrie.pt", seed=90, use_trie=False)
     for f in sorted(os.listdir(OUT)):

@@ -80,15 +80,24 @@ def ref_genrec_package():
         sys.modules.update(saved)
 
 
+def ref_transformer():
+    """The reference's genrec.modules.transformer module (T5Attention, ...)."""
+    return _ref_module("genrec.modules.transformer")
+
+
 def ref_tiger():
     """The reference's genrec.models.tiger module (Tiger, build_trie), imported like ref_genrec_package()."""
+    return _ref_module("genrec.models.tiger")
+
+
+def _ref_module(name: str):
     _install_stubs()
     saved = {k: v for k, v in sys.modules.items() if k == "genrec" or k.startswith("genrec.")}
     for k in saved:
         del sys.modules[k]
     sys.path.insert(0, REF_ROOT)
     try:
-        return importlib.import_module("genrec.models.tiger")
+        return importlib.import_module(name)
     finally:
         sys.path.remove(REF_ROOT)
         for k in [k for k in sys.modules if k == "genrec" or k.startswith("genrec.")]:

@@ -177,3 +177,24 @@ def test_trie_csr_equals_the_dict_trie():
             stack.append((nd[k], child[e]))
     assert seen == t.n_nodes
     assert TrieCSR.build(valid.view(100, 3, 3)).child_tok.tolist() == tok          # (B, T, C) input, tiger.py:58-60
+
+
+def test_t5_attention_oracle_vs_reference_golden(golden):
+    """oracle/t5_attention.py reproduces the unmodified reference's T5Attention (outputs, every gradient) exactly, and the bucket map of
+    the product's host code equals the reference formula (transformer.py:13-41)."""
+    from oracle import t5_attention as ot
+    from genrec_b200.t5_attention import relative_position_buckets
+    g = golden("t5_attention.pt")
+    for name, c in g["cases"].items():
+        x = c["x"].clone().requires_grad_(True)
+        sd = {k: v.clone().requires_grad_(True) for k, v in c["state_dict"].items()}
+        ctx = c["ctx"].clone().requires_grad_(True) if c["cross"] else None
+        mask = torch.nn.Transformer.generate_square_subsequent_mask(x.shape[1]) if c["causal"] else None
+        out = ot.t5_attention_forward(x, ctx, ctx, sd, c["heads"], c["cross"], mask, c["pad"])
+        out.backward(c["dy"])
+        assert torch.equal(out, c["out"]) and torch.equal(x.grad, c["dx"]), name
+        for k in sd:
+            assert torch.equal(sd[k].grad, c["grads"][k]), (name, k)
+    for lq, lk in ((37, 37), (9, 21), (200, 300), (1, 5)):
+        i = torch.arange(lq)[:, None]; j = torch.arange(lk)[None, :]
+        assert torch.equal(ot.bucket_of(j - i), relative_position_buckets(lq, lk).long()[(j - i) + lq - 1])
