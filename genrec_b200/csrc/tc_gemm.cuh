@@ -22,6 +22,7 @@ namespace grb {
 
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM sub-partition: each converts 4 / (TC_EPI_WARPS / 4) 32-column chunks of the tile
 constexpr int TC_EPI_CPW = 4 / (TC_EPI_WARPS / 4);   // chunks per warp (16 warps measured slower here: register spills)
+static_assert(TC_EPI_CPW == 2, "a warp's 2 x 32 columns are one 64-column bf16 store box");
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA, MMA, epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB per operand per stage
 constexpr int TC_STAGE_OUT_BYTES = 64 * 1024;   // epilogue staging: 2 x bf16 [128x128] or 1 x fp32 [128x128], 128B-swizzled boxes
@@ -285,6 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (row < sh.M && nvalid > 0) epi.preload(row, col0, nvalid, pre[ci]);
                 }
             }
+            if constexpr (Epi::kOut != 0) {
+                if (lane == 0) tma_store_wait_read1();   // this warp's store from two tiles ago has finished reading its staging piece
+                __syncwarp();
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             unsigned char* sOut = sOut0 + acc * TC_STAGE_OUT_BYTES;  // staging buffer alternates with the accumulator
@@ -351,30 +356,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMA warp may start the next-but-one tile
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if constexpr (Epi::kOut != 0) {
+                // Every epilogue warp owns rows 32*sub .. +31 of the 64-column (bf16) / 2 x 32-column (fp32) slab cq of the staging
+                // tile - a contiguous, swizzle-aligned 4 KB piece of each 128-row box - and stores it with its OWN bulk store (tensor-map
+                // box = 32 rows): no CTA-wide barrier per tile, the warps drift apart freely.  Buffer reuse is guarded per warp by
+                // `wait_group.read 1` at the top of the tile (the piece written two tiles ago has been read).
                 fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-                epi_bar_sync();
-                if (warp == 2 && lane == 0) {
+                __syncwarp();
+                if (lane == 0 && m0 + sub * 32 < sh.M) {
                     if constexpr (Epi::kOut == 3) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (n0 + c * 32 < sh.N) tma_store_2d(&tmC0, sOut + c * 16384, n0 + c * 32, m0);
+                        for (int ci = 0; ci < TC_EPI_CPW; ++ci) {
+                            const int c = cq * TC_EPI_CPW + ci;
+                            if (n0 + c * 32 < sh.N) tma_store_2d(&tmC0, sOut + c * 16384 + sub * 4096, n0 + c * 32, m0 + sub * 32);
+                        }
                     } else {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (n0 + h * 64 < sh.N) {
-                                tma_store_2d(&tmC0, sOut + h * 16384, n0 + h * 64, m0);
-                                if constexpr (Epi::kOut == 2) tma_store_2d(&tmC1, sOut + 32768 + h * 16384, n0 + h * 64, m0);
-                            }
+                        if (n0 + cq * 64 < sh.N) {
+                            tma_store_2d(&tmC0, sOut + cq * 16384 + sub * 4096, n0 + cq * 64, m0 + sub * 32);
+                            if constexpr (Epi::kOut == 2) tma_store_2d(&tmC1, sOut + 32768 + cq * 16384 + sub * 4096, n0 + cq * 64, m0 + sub * 32);
                         }
                     }
-                    tma_store_commit();
-                    tma_store_wait_read1();  // the OTHER staging buffer (previous tile's group) has been read -> reusable
                 }
-                epi_bar_sync();
+                if (lane == 0) tma_store_commit();
             }
         }
+        if (Epi::kOut != 0 && lane == 0) tma_store_wait_read();  // smem must outlive this warp's last bulk stores
     }
-    if (Epi::kOut != 0 && warp == 2 && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk stores
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -664,11 +670,11 @@ inline cudaError_t launch_tc_gemm(const bf16* A, const bf16* B, int M, int N, in
     if (Epi::kOut == 0) {
         tmC0 = tmA; tmC1 = tmA;
     } else if (Epi::kOut == 3) {
-        ok = ok && make_tmap(&tmC0, out0, true, M, N, ldo, 32, TC_BM);
+        ok = ok && make_tmap(&tmC0, out0, true, M, N, ldo, 32, 32);     // store boxes: 32 rows, one per epilogue warp
         tmC1 = tmC0;
     } else {
-        ok = ok && make_tmap(&tmC0, out0, false, M, N, ldo, 64, TC_BM);
-        if (Epi::kOut == 2) ok = ok && make_tmap(&tmC1, out1, false, M, N, ldo, 64, TC_BM);
+        ok = ok && make_tmap(&tmC0, out0, false, M, N, ldo, 64, 32);
+        if (Epi::kOut == 2) ok = ok && make_tmap(&tmC1, out1, false, M, N, ldo, 64, 32);
         else tmC1 = tmC0;
     }
     if constexpr (Epi::kAux) {
