@@ -366,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not args.skip_roofline:
         roof = block_roofline(model, B, L, dev, K)
     cpu = None
-    if rank == 0 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu:      # reported baselines: single-GPU runs only (the other ranks would idle)
         try:
             r = cpu_arm(args.cpu_batch, L, args.cpu_seconds)
             cpu = dict(value=r["seq_per_s"], unit=UNIT, cores=r["threads"], kind="port",
@@ -376,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
     used_graph = graph is not None
     eager = None
-    if rank == 0 and not args.skip_eager:
+    if rank == 0 and world == 1 and not args.skip_eager:
         used_graph = graph is not None
         graph = None
         torch.cuda.empty_cache()
