@@ -386,6 +386,8 @@ def run_ours(args, rank, world, local_rank):
                          what="the reference's algorithm as PyTorch eager + autocast(bf16) on this same GPU (oracle restatement, dropout 0, Adam)")
         except Exception as e:  # noqa: BLE001
             eager = dict(value=None, unit=UNIT, what=f"failed: {type(e).__name__}: {e}")
+    if world > 1:
+        dist.barrier()      # rank 0 measured its extras alone: tear the process group down together
     if rank != 0:
         return
     gb = B * world
