@@ -106,3 +106,37 @@ def test_head_wide_logit_range():
     for name, a, b in zip(("dx", "dln_g", "dln_b", "dtable"), got[1:], ref[1:]):
         assert torch.isfinite(a).all(), name
         assert relerr(a, b) < 3e-2, (name, relerr(a, b))
+
+
+def _overflow_case():
+    """Every row's logit for class 2500 sits ~190 nats above everything else (LayerNorm bias = 1 along a table row of 1.5s), far from
+    the probe tile (classes 0..127) and - for all but a handful of rows - not the target."""
+    x, ln_g, ln_b, table, tg = _case(2, 40, 128, 3000, seed=33, frac_ignored=0.0)
+    ln_g = torch.ones(128); ln_b = torch.ones(128)
+    table = 0.01 * table
+    table[2500] = 1.5
+    tg[tg == 2500] = 7
+    return x, ln_g, ln_b, table, tg
+
+
+def test_one_sweep_range_limit_is_loud_and_exact_mode_has_none():
+    """the one-sweep kernel's exponent shift is max(probe tile, target logit); a class beating both by more than ~98 nats
+    overflows that row - the loss comes out non-finite, never silently wrong - and GRB_CE=exact computes the same case exactly."""
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from tests.test_head_gpu import _overflow_case, _ours\n"
+        "out = _ours(*_overflow_case())\n"
+        "torch.save(out, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for mode in ("", "exact"):
+        path = f"/tmp/_head_overflow_{mode or 'default'}.pt"
+        env = dict(os.environ, GRB_CE=mode)
+        if not mode:
+            env.pop("GRB_CE")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[mode] = torch.load(path)
+    assert not torch.isfinite(res[""][0])                            # loud
+    ref = _reference(*_overflow_case())
+    got = res["exact"]
+    assert torch.isfinite(got[0]) and abs(got[0].item() - ref[0].item()) < 2e-3 * abs(ref[0].item())
+    assert relerr(got[1], ref[1]) < 3e-2 and relerr(got[4], ref[4]) < 3e-2
