@@ -198,3 +198,14 @@ def test_t5_attention_oracle_vs_reference_golden(golden):
     for lq, lk in ((37, 37), (9, 21), (200, 300), (1, 5)):
         i = torch.arange(lq)[:, None]; j = torch.arange(lk)[None, :]
         assert torch.equal(ot.bucket_of(j - i), relative_position_buckets(lq, lk).long()[(j - i) + lq - 1])
+
+
+def test_trie_csr_edge_shapes():
+    """One item, a 1-D item, items sharing every prefix: node and edge counts of the CSR trie (tiger.py:49-69 semantics)."""
+    from genrec_b200.tiger_decode import TrieCSR
+    t = TrieCSR.build(torch.tensor([4, 2, 9]))                       # 1-D: one sequence (tiger.py:61-62)
+    assert t.n_nodes == 4 and t.child_tok.tolist() == [4, 2, 9] and t.child_off.tolist() == [0, 1, 2, 3, 3]
+    t = TrieCSR.build(torch.tensor([[1, 1, 1], [1, 1, 1], [1, 1, 2]]))
+    assert t.n_nodes == 5 and t.child_off.tolist() == [0, 1, 2, 4, 4, 4] and t.child_tok.tolist() == [1, 1, 1, 2]
+    t = TrieCSR.build(torch.tensor([[0, 5], [3, 5], [0, 4]]))
+    assert t.child_tok.tolist() == [0, 3, 4, 5, 5] and t.child_node.tolist() == [1, 2, 3, 4, 5]
